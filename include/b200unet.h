@@ -4,21 +4,24 @@
  * point replaces one operator call the reference makes through torch.nn on its hot path (file:line are
  * relative to minghanz/pytorch-unet):
  *
- *   conv3x3_fwd / dgrad / wgrad   nn.Conv2d(k=3, padding=int(padding)) + nn.ReLU      unet.py:92-93, 97-98
- *                                 (+ center_crop + torch.cat folded into the consumer  unet.py:152-163)
- *   convt2x2_fwd / dgrad / wgrad  nn.ConvTranspose2d(k=2, s=2)                         unet.py:143, 173
- *   conv1x1_*  (same entry points as conv3x3 with taps = 1)   nn.Conv2d(k=1)           unet.py:147, 177
- *   maxpool2x2_fwd / bwd          F.max_pool2d(x, 2)                                   unet.py:79
- *   bilinear_up2x_fwd / bwd       nn.Upsample(mode='bilinear', scale_factor=2)         unet.py:146, 176
- *   bn_fwd_train / bn_fwd_eval / bn_bwd   nn.BatchNorm2d (after the ReLU)              unet.py:95, 100
- *   head_fwd / head_ce_fwd_bwd    nn.Conv2d(k=1) head [+ReLU] and F.cross_entropy      unet.py:65-71, 84; README.md:58
- *   nchw_to_nhwc / nhwc_to_nchw, pack_*   boundary layout / precision transforms
+ *   conv_fwd / conv_dgrad / conv_wgrad   nn.Conv2d(k=3, padding=int(padding)) + nn.ReLU   unet.py:92-93, 97-98
+ *                                        (+ center_crop + torch.cat folded in: two sources  unet.py:152-163)
+ *                                        taps = 1: nn.Conv2d(k=1)                           unet.py:147, 177
+ *   convt_fwd / convt_dgrad / convt_wgrad  nn.ConvTranspose2d(k=2, s=2)                    unet.py:143, 173
+ *   maxpool2x2_fwd / bwd                 F.max_pool2d(x, 2)                                unet.py:79
+ *   bilinear_up2x_fwd / bwd              nn.Upsample(mode='bilinear', scale_factor=2)      unet.py:146, 176
+ *   bn_fwd_train / bn_fwd_eval / bn_bwd  nn.BatchNorm2d (after the ReLU)                   unet.py:95, 100
+ *   head_fwd / head_bwd                  nn.Conv2d(k=1) head [+ReLU]                       unet.py:65-71, 84
+ *   head_ce_fwd / head_ce_bwd            head fused with F.cross_entropy                   README.md:58
+ *   nchw_f32_to_nhwc_bf16, nhwc_bf16_to_nchw_f32, pack_*   boundary layout / precision transforms
  *
  * Conventions
- *   - Activations and activation gradients are bf16, NHWC ("pixels x channels"), described by b200_view.
+ *   - Activations and activation gradients are bf16, NHWC ("pixels x channels"), described by b200_view.  A
+ *     view may be a window of a larger tensor (pointer offset + strides): this is how the skip connection's
+ *     center crop is expressed — no cropped or concatenated tensor is ever materialised.
  *   - Parameters cross the boundary in the reference's state_dict layouts (fp32 OIHW etc.); packed bf16
- *     copies are produced by the pack_* entry points.  Parameter gradients are returned fp32 in state_dict
- *     layout.
+ *     copies for the tensor-core kernels are produced by the pack_* entry points.  Parameter gradients are
+ *     returned fp32 in state_dict layout.
  *   - The caller owns every buffer (inputs, outputs, workspace).  The library never allocates device memory,
  *     never synchronises, and launches only on the stream passed in -> CUDA-graph capturable.
  *   - Return value: 0 = ok; < 0 = argument / shape / alignment error detected before launch; > 0 = cudaError_t.
@@ -35,51 +38,50 @@
 extern "C" {
 #endif
 
-#define B200UNET_ABI_VERSION 1
+#define B200UNET_ABI_VERSION 2
 
-/* Strided NHWC view of a bf16 (or, where stated, fp32) tensor.  Channel stride is 1.  Strides in elements. */
+/* Strided NHWC view of a bf16 tensor.  Channel stride is 1.  Strides in elements. */
 typedef struct {
   void* ptr;
   int32_t n, h, w, c;
   int64_t stride_n, stride_h, stride_w;
 } b200_view;
 
-/* implementation selector for the convolution family */
+/* implementation selector for the convolution family.  AUTO = tcgen05 kernel whenever the shape allows it
+ * (every source / destination channel count a multiple of 8 and 16-byte aligned rows), else the CUDA-core one. */
 enum { B200_IMPL_AUTO = 0, B200_IMPL_DIRECT = 1, B200_IMPL_UMMA = 2 };
 
-/* ---- conv (3x3 or 1x1), forward.  y = act(conv(cat(src0, crop(src1)), W) + b)
- * src[i] are read at (h + crop_y[i] - pad + r, w + crop_x[i] - pad + s); zero outside the view.
+/* ---- conv (3x3 or 1x1), forward.  y = act(conv(cat(src[0], src[1]), W) + b)
+ * src[i]: the (already center-cropped) input windows, all of extent n x (h_out + (k-1) - 2 pad) x (w_out + ...).
+ * Reads outside a window are zero (that is the zero padding of nn.Conv2d applied to the cropped tensor).
  * w_packed: bf16 [cout][taps][kpad], kpad = sum_i roundup(src[i].c, 64)   (pack_conv_weight, mode 0)      */
 typedef struct {
   b200_view src[2];
   int32_t num_src;
-  int32_t crop_y[2], crop_x[2];
   int32_t taps; /* 9 or 1 */
-  int32_t pad;  /* 0, 1 (or 2 for the transposed pass) */
-  const void* w_packed;
-  const float* bias; /* may be NULL */
+  int32_t pad;  /* 0 or 1 */
+  const void* w_packed; /* tcgen05 path */
+  const float* w_f32;   /* fp32 OIHW master weights: CUDA-core path */
+  const float* bias;    /* may be NULL */
   int32_t relu;
-  b200_view dst;     /* n, h, w = output extent; c = cout */
-  const float* w_f32; /* fp32 OIHW master weights: used by the direct (CUDA-core) implementation */
+  b200_view dst;        /* n, h, w = output extent; c = cout */
   int32_t impl;
 } b200_conv_fwd_params;
 
 /* ---- conv backward-data.  dx = conv_transpose(dz, W) [* (mask > 0)]
  * dz view: n, h, w = forward output extent; c = cout.  dx is written to up to two destinations by input
- * channel: channels [0, dst[0].c) -> dst[0], the rest -> dst[1] at offset (dst_off_y, dst_off_x) (the crop
- * of the skip connection).  mask[i], if not NULL, is a bf16 tensor laid out exactly like dst[i]; outputs
- * where mask <= 0 are zeroed (ReLU backward of the producer, unet.py:93).
- * w_packed: bf16 [cin_pad...]: pack_conv_weight mode 1 ([cin][taps flipped][cout_pad64]).                 */
+ * channel: channels [0, dst[0].c) -> dst[0], the rest -> dst[1] (a window of the skip tensor's gradient).
+ * mask[i], if not NULL, is a bf16 tensor laid out exactly like dst[i]; outputs where mask <= 0 are zeroed
+ * (ReLU backward of the producer, unet.py:93).
+ * w_packed: pack_conv_weight mode 1 ([cin_total][taps flipped][roundup(cout, 64)]).                        */
 typedef struct {
   b200_view dz;
   int32_t taps, pad;
   const void* w_packed;
+  const float* w_f32;
   b200_view dst[2];
   int32_t num_dst;
-  int32_t dst_off_y[2], dst_off_x[2];
   const void* mask[2];
-  const float* w_f32;
-  int32_t cin_total;
   int32_t impl;
 } b200_conv_dgrad_params;
 
@@ -90,7 +92,6 @@ typedef struct {
   b200_view dz;
   b200_view src[2];
   int32_t num_src;
-  int32_t crop_y[2], crop_x[2];
   int32_t taps, pad;
   float* dw_f32;
   float* db_f32;
@@ -98,14 +99,14 @@ typedef struct {
 } b200_conv_wgrad_params;
 
 /* ---- ConvTranspose2d(k=2, s=2).  y[n, 2i+a, 2j+b, o] = bias[o] + sum_c x[n,i,j,c] * W[c,o,a,b]
- * w_packed (fwd):  bf16 [(a,b,o)][roundup(cin,64)]       (pack_convt_weight mode 0)
- * w_packed (dgrad): bf16 [cin][(a,b,o) padded]           (pack_convt_weight mode 1)                        */
+ * w_packed (fwd):  bf16 [(a*2+b)*cout + o][roundup(cin,64)]   (pack_convt_weight mode 0)
+ * w_packed (dgrad): bf16 [cin][a*2+b][roundup(cout,64)]       (pack_convt_weight mode 1)                   */
 typedef struct {
   b200_view x;  /* n,h,w,cin */
   b200_view y;  /* n,2h,2w,cout */
   const void* w_packed;
-  const float* bias;
   const float* w_f32; /* [cin][cout][2][2] */
+  const float* bias;
   int32_t impl;
 } b200_convt_fwd_params;
 
@@ -113,8 +114,8 @@ typedef struct {
   b200_view dy; /* n,2h,2w,cout */
   b200_view dx; /* n,h,w,cin */
   const void* w_packed;
-  const void* mask; /* optional, laid out like dx */
   const float* w_f32;
+  const void* mask; /* optional, laid out like dx */
   int32_t impl;
 } b200_convt_dgrad_params;
 
@@ -130,6 +131,7 @@ int b200unet_abi_version(void);
 const char* b200unet_last_error(void);
 /* 1 if the tcgen05 path can run on the current device (sm_100) */
 int b200unet_device_ok(void);
+int b200unet_num_sms(void);
 
 int b200unet_conv_fwd(const b200_conv_fwd_params* p, void* stream);
 int b200unet_conv_dgrad(const b200_conv_dgrad_params* p, void* stream);
@@ -141,13 +143,18 @@ int b200unet_convt_dgrad(const b200_convt_dgrad_params* p, void* stream);
 size_t b200unet_convt_wgrad_workspace_bytes(const b200_convt_wgrad_params* p);
 int b200unet_convt_wgrad(const b200_convt_wgrad_params* p, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Which implementation AUTO resolves to for these parameters (B200_IMPL_DIRECT or B200_IMPL_UMMA). */
+int b200unet_conv_fwd_impl(const b200_conv_fwd_params* p);
+int b200unet_conv_dgrad_impl(const b200_conv_dgrad_params* p);
+int b200unet_conv_wgrad_impl(const b200_conv_wgrad_params* p);
+
 /* ---- weight packing (fp32 state_dict layout -> bf16 GEMM operand layout)
  * conv: w [cout][cin_total][k][k]; src_c[i] = channels of source i (cin_total = sum).
  *   mode 0 (fprop): out [cout][taps][kpad],             kpad = sum roundup(src_c[i], 64)
  *   mode 1 (dgrad): out [cin_total][taps][roundup(cout,64)], taps spatially flipped
  * convt: w [cin][cout][2][2]
  *   mode 0 (fwd):   out [(a*2+b)*cout + o][roundup(cin,64)]
- *   mode 1 (dgrad): out [cin][ (a, b, o) ] = [cin][4*cout]  (cout % 16 == 0 assumed by the tcgen05 path)      */
+ *   mode 1 (dgrad): out [cin][a*2+b][roundup(cout,64)]                                                     */
 size_t b200unet_pack_conv_weight_bytes(int cout, int num_src, const int* src_c, int taps, int mode);
 int b200unet_pack_conv_weight(const float* w, int cout, int num_src, const int* src_c, int taps, int mode,
                               void* out, void* stream);
@@ -155,23 +162,25 @@ size_t b200unet_pack_convt_weight_bytes(int cin, int cout, int mode);
 int b200unet_pack_convt_weight(const float* w, int cin, int cout, int mode, void* out, void* stream);
 
 /* ---- F.max_pool2d(x, 2).  idx8: uint8 code a*2+b of the arg-max inside each window (first max in row-major
- * order wins, NaN propagates — ATen semantics); idx64 (optional, may be NULL): int64 flat h*W+w index in the
- * input plane, exactly what F.max_pool2d(..., return_indices=True) yields, stored NHWC like y.            */
+ * order wins, NaN propagates — ATen semantics), dense [n][h/2][w/2][c]; idx64 (optional, may be NULL): int64
+ * flat h*W+w index in the input plane, exactly what F.max_pool2d(..., return_indices=True) yields, stored
+ * NHWC like idx8.                                                                                          */
 int b200unet_maxpool2x2_fwd(const b200_view* x, const b200_view* y, uint8_t* idx8, int64_t* idx64, void* stream);
-/* dx = scatter(dy, idx) [+ add (a view of the same extent as dx restricted to a crop window)] [* (mask > 0)]
- * add: optional gradient already present in dx's crop window [add_y, add_y+add.h) x [add_x, add_x+add.w):
- *      the skip-connection gradient (unet.py:152-163 backward).  mask: optional bf16 like dx.             */
+/* dx = scatter(dy, idx) + add (inside its window) , then * (mask > 0).
+ * add: optional view of extent n x ah x aw x c placed at (add_y, add_x) of dx: the gradient that reached the
+ *      skip connection through the center crop (unet.py:152-163 backward).  It may alias dx's own memory.
+ * mask: optional bf16 laid out like dx.                                                                    */
 int b200unet_maxpool2x2_bwd(const b200_view* dy, const uint8_t* idx8, const b200_view* dx, const b200_view* add,
                             int add_y, int add_x, const void* mask, void* stream);
 
-/* ---- nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False) */
+/* ---- nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False); mask optional, laid out like dx */
 int b200unet_bilinear_up2x_fwd(const b200_view* x, const b200_view* y, void* stream);
-int b200unet_bilinear_up2x_bwd(const b200_view* dy, const b200_view* dx, void* stream);
+int b200unet_bilinear_up2x_bwd(const b200_view* dy, const b200_view* dx, const void* mask, void* stream);
 
 /* ---- nn.BatchNorm2d over the post-ReLU tensor.
  * train: batch statistics over n*h*w (biased variance for normalisation), writes save_mean / save_invstd
- * (fp32 [c]) for backward and updates running_mean / running_var (momentum, unbiased) in place.
- * workspace: b200unet_bn_workspace_bytes(c).                                                              */
+ * (fp32 [c]) for backward and updates running_mean / running_var (momentum, unbiased) in place (either may be
+ * NULL).  workspace: b200unet_bn_workspace_bytes(c).                                                       */
 size_t b200unet_bn_workspace_bytes(int c);
 int b200unet_bn_fwd_train(const b200_view* x, const b200_view* y, const float* gamma, const float* beta,
                           float* running_mean, float* running_var, float momentum, float eps, float* save_mean,
@@ -184,27 +193,32 @@ int b200unet_bn_bwd(const b200_view* x, const b200_view* dy, const b200_view* dx
                     const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, int relu_mask,
                     void* workspace, size_t workspace_bytes, void* stream);
 
-/* ---- head: 1x1 conv to n_classes (<= 8) [+ReLU], logits fp32 NCHW (the module's return value) */
+/* ---- head: 1x1 conv to n_classes (<= 8) [+ReLU]; logits fp32 NCHW (the module's return value).
+ * w [k][c], b [k] fp32.  workspace for every head entry point: b200unet_head_workspace_bytes().            */
+size_t b200unet_head_workspace_bytes(int c, int n_classes);
 int b200unet_head_fwd(const b200_view* x, const float* w, const float* b, int n_classes, int relu,
                       float* logits_nchw, void* stream);
-/* head backward from an upstream fp32 NCHW gradient: dx (bf16, like x) [* (mask>0)], dw [k][c], db [k] */
-int b200unet_head_bwd(const b200_view* x, const float* w, int n_classes, int relu, const float* logits_nchw,
+/* backward from an upstream fp32 NCHW gradient: dx (bf16 like x, may be NULL) [* (mask>0)], dw [k][c], db [k] */
+int b200unet_head_bwd(const b200_view* x, const float* w, const float* b, int n_classes, int relu,
                       const float* dlogits_nchw, const b200_view* dx, const void* mask, float* dw, float* db,
                       void* workspace, size_t workspace_bytes, void* stream);
-/* fused head + F.cross_entropy(mean): loss (fp32 scalar, device), optional logits, dx/dw/db in one pass.
- * labels: int64 [n][h][w].  workspace: b200unet_head_workspace_bytes().                                   */
-size_t b200unet_head_workspace_bytes(int c, int n_classes);
-int b200unet_head_ce_fwd_bwd(const b200_view* x, const float* w, const float* b, int n_classes, int relu,
-                             const int64_t* labels, float* loss, float* logits_nchw, const b200_view* dx,
-                             const void* mask, float* dw, float* db, void* workspace, size_t workspace_bytes,
-                             void* stream);
+/* head fused with F.cross_entropy(reduction='mean', ignore_index=-100).  labels: int64 [n][h][w].
+ * fwd: loss (fp32 device scalar, may be NULL), optional logits, ce_state[2] = {loss, 1/valid_count} kept for bwd.
+ * bwd: grad_scale = device pointer to d(loss) (NULL = 1); recomputes the logits from x.                     */
+int b200unet_head_ce_fwd(const b200_view* x, const float* w, const float* b, int n_classes, int relu,
+                         const int64_t* labels, float* loss, float* logits_nchw, float* ce_state, void* workspace,
+                         size_t workspace_bytes, void* stream);
+int b200unet_head_ce_bwd(const b200_view* x, const float* w, const float* b, int n_classes, int relu,
+                         const int64_t* labels, const float* grad_scale, const float* ce_state, const b200_view* dx,
+                         const void* mask, float* dw, float* db, void* workspace, size_t workspace_bytes,
+                         void* stream);
 
 /* ---- boundary transforms */
 int b200unet_nchw_f32_to_nhwc_bf16(const float* src, const b200_view* dst, void* stream);
 int b200unet_nhwc_bf16_to_nchw_f32(const b200_view* src, float* dst, void* stream);
-/* db[c] = sum over n,h,w of dz (fp32 [c]); workspace b200unet_bn_workspace_bytes(c) */
+/* out[c] = sum over n,h,w of dz (fp32 [c]); workspace b200unet_bn_workspace_bytes(c) */
 int b200unet_channel_sum(const b200_view* dz, float* out, void* workspace, size_t workspace_bytes, void* stream);
-/* y = (mask > 0) ? x : 0, in place allowed */
+/* y = (mask > 0) ? x : 0, in place allowed; mask laid out like y */
 int b200unet_relu_mask(const b200_view* x, const void* mask, const b200_view* y, void* stream);
 
 #ifdef __cplusplus

@@ -1,0 +1,389 @@
+"""Drop-in `UNet` for minghanz/pytorch-unet on B200: same constructor, `forward` contract and `state_dict` schema
+as the reference (unet.py:8-84 / unet_original.py:8-75), but forward and backward run on the hand-written sm_100a
+kernels of libb200unet.so through `b200unet.ops`.  Nothing here falls back to torch.nn compute: the nn.Conv2d /
+nn.BatchNorm2d / nn.ConvTranspose2d children exist only as parameter containers, so that parameter names, shapes,
+initialisation order and checkpoints are those of the reference.
+
+Internals: activations are NHWC bf16; the whole network is ONE autograd node (`_UNetFunction`) whose backward is a
+hand-scheduled reverse pass, so that
+  * the center-crop + concat of the skip connection (unet.py:152-163) is never materialised: the consumer
+    convolution reads two windows, its backward-data writes two destinations;
+  * every ReLU backward is fused into the kernel that produces the gradient (mask operand), every bias/ReLU
+    forward into the convolution epilogue;
+  * the gradient of a skip tensor = pool backward + the window written by the decoder, summed in one kernel;
+  * weight gradients are produced in reverse-forward order into one flat fp32 arena, bucket by bucket, which is
+    what the data-parallel wrapper all-reduces while the rest of the backward is still running.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import ops
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# parameter containers with the reference's module tree (names are part of the checkpoint format)
+# ---------------------------------------------------------------------------------------------------------------
+class UNetConvBlock(nn.Module):
+    """Conv3x3 -> ReLU -> [BatchNorm] -> Conv3x3 -> ReLU -> [BatchNorm]   (unet.py:87-106)."""
+
+    def __init__(self, in_size: int, out_size: int, padding: bool, batch_norm: bool):
+        super().__init__()
+        block: List[nn.Module] = [nn.Conv2d(in_size, out_size, kernel_size=3, padding=int(padding)), nn.ReLU()]
+        if batch_norm:
+            block.append(nn.BatchNorm2d(out_size))
+        block += [nn.Conv2d(out_size, out_size, kernel_size=3, padding=int(padding)), nn.ReLU()]
+        if batch_norm:
+            block.append(nn.BatchNorm2d(out_size))
+        self.block = nn.Sequential(*block)
+        self.batch_norm = batch_norm
+
+    def convs(self) -> Tuple[nn.Conv2d, nn.Conv2d]:
+        return (self.block[0], self.block[3 if self.batch_norm else 2])
+
+    def bns(self) -> Tuple[Optional[nn.BatchNorm2d], Optional[nn.BatchNorm2d]]:
+        return (self.block[2], self.block[5]) if self.batch_norm else (None, None)
+
+
+class _UpBase(nn.Module):
+    def __init__(self, up_in: int, up_out: int, block_in: int, block_out: int, up_mode: str, padding: bool,
+                 batch_norm: bool):
+        super().__init__()
+        if up_mode == "upconv":
+            self.up = nn.ConvTranspose2d(up_in, up_out, kernel_size=2, stride=2)
+        else:
+            self.up = nn.Sequential(nn.Upsample(mode="bilinear", scale_factor=2), nn.Conv2d(up_in, up_out, kernel_size=1))
+        self.conv_block = UNetConvBlock(block_in, block_out, padding, batch_norm)
+        self.up_mode = up_mode
+
+
+class UNetUpBlock(_UpBase):
+    """Paper decoder block (unet.py:139-166, unet_original.py:100-127): up halves the channels."""
+
+    def __init__(self, in_size: int, out_size: int, up_mode: str, padding: bool, batch_norm: bool):
+        super().__init__(in_size, out_size, in_size, out_size, up_mode, padding, batch_norm)
+
+
+class UNetUpBlockDeep(_UpBase):
+    """Decoder block `unet.py` actually instantiates (unet.py:169-199): up keeps the channels."""
+
+    def __init__(self, in_size: int, skip_in_size: int, out_size: int, up_mode: str, padding: bool, batch_norm: bool):
+        super().__init__(in_size, in_size, in_size + skip_in_size, out_size, up_mode, padding, batch_norm)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the autograd node
+# ---------------------------------------------------------------------------------------------------------------
+class _Tape:
+    """What one forward call keeps for its backward."""
+
+    def __init__(self):
+        self.blocks: Dict[str, dict] = {}
+        self.pools: List[dict] = []
+        self.ups: List[dict] = []
+        self.head: dict = {}
+
+
+def _crop_window(bridge: torch.Tensor, h: int, w: int) -> Tuple[torch.Tensor, int, int]:
+    """center_crop (unet.py:152-158) as a strided window, no copy."""
+    dy, dx = (bridge.shape[1] - h) // 2, (bridge.shape[2] - w) // 2
+    return bridge[:, dy:dy + h, dx:dx + w, :], dy, dx
+
+
+class _UNetFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model: "UNet", x: torch.Tensor, labels: Optional[torch.Tensor], *params: torch.Tensor):
+        names = model._param_names
+        P = dict(zip(names, params))
+        keep = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        tape = _Tape() if keep else None
+        out = model._run_forward(x, labels, P, tape)
+        ctx.model, ctx.tape, ctx.P, ctx.labels = model, tape, P, labels
+        ctx.set_materialize_grads(False)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        model, tape = ctx.model, ctx.tape
+        if tape is None:
+            raise RuntimeError("b200unet: backward called on a forward that did not record (no_grad / frozen)")
+        ctx.tape = None
+        if grad_out is None:
+            return (None, None, None) + tuple(None for _ in model._param_names)
+        grads = model._run_backward(tape, ctx.P, ctx.labels, grad_out)
+        return (None, None, None) + tuple(grads.get(n) for n in model._param_names)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the module
+# ---------------------------------------------------------------------------------------------------------------
+class UNet(nn.Module):
+    """U-Net (Ronneberger et al. 2015) with the reference's options.
+
+    Positional arguments are the reference's (unet.py:9-19): in_channels, n_classes, depth, wf, padding, batch_norm,
+    up_mode, non_neg.  `up_block` selects the decoder: 'paper' = UNetUpBlock (the graph of unet_original.py, the
+    7-argument signature in README.md:14-15) or 'deep' = UNetUpBlockDeep (what unet.py:60 builds).  Output: fp32
+    NCHW logits, differentiable w.r.t. the parameters.
+    """
+
+    def __init__(self, in_channels: int = 1, n_classes: int = 2, depth: int = 5, wf: int = 6, padding: bool = False,
+                 batch_norm: bool = False, up_mode: str = "upconv", non_neg: bool = False, up_block: str = "paper",
+                 conv_impl: int = ops.IMPL_AUTO):
+        super().__init__()
+        assert up_mode in ("upconv", "upsample")  # unet.py:45
+        assert up_block in ("paper", "deep")
+        self.padding = padding
+        self.depth = depth
+        self.batch_norm = batch_norm
+        self.up_mode = up_mode
+        self.non_neg = non_neg
+        self.up_block = up_block
+        self.n_classes = n_classes
+        self.in_channels = in_channels
+        self.conv_impl = conv_impl
+        prev = in_channels
+        self.down_path = nn.ModuleList()
+        for i in range(depth):
+            self.down_path.append(UNetConvBlock(prev, 2 ** (wf + i), padding, batch_norm))
+            prev = 2 ** (wf + i)
+        self.up_path = nn.ModuleList()
+        for i in reversed(range(depth - 1)):
+            if up_block == "paper":
+                self.up_path.append(UNetUpBlock(prev, 2 ** (wf + i), up_mode, padding, batch_norm))
+                prev = 2 ** (wf + i)
+            else:  # unet.py:60 — prev_channels is never updated (unet.py:63 is commented out)
+                self.up_path.append(UNetUpBlockDeep(prev, 2 ** (wf + i), prev, up_mode, padding, batch_norm))
+        if non_neg:  # unet.py:65-69
+            self.last = nn.Sequential(nn.Conv2d(prev, n_classes, kernel_size=1), nn.ReLU())
+        else:
+            self.last = nn.Conv2d(prev, n_classes, kernel_size=1)
+        self._param_names = [n for n, _ in self.named_parameters()]
+        # hooks for the data-parallel wrapper: grad arena allocator + "these gradients are final" callback
+        self._grad_alloc: Optional[Callable[[str, Tuple[int, ...], torch.device], torch.Tensor]] = None
+        self._grad_ready: Optional[Callable[[str], None]] = None
+        self._pack_cache: Dict[Tuple[str, int], Tuple[int, int, torch.Tensor]] = {}
+
+    # ---------------------------------------------------------------- public API
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self._apply_fn(x, None)
+
+    def loss(self, x: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        """F.cross_entropy(self(x), target) (README.md:57-58) with the classifier fused into the loss kernel: the
+        logits never touch HBM.  Returns the scalar mean loss (ignore_index = -100)."""
+        return self._apply_fn(x, target)
+
+    def _apply_fn(self, x, labels):
+        if not x.is_cuda:
+            raise RuntimeError("b200unet.UNet runs on CUDA (sm_100a) only: there is no CPU path")
+        params = [p for _, p in self.named_parameters()]
+        return _UNetFunction.apply(self, x, labels, *params)
+
+    # ---------------------------------------------------------------- helpers
+    def _packed(self, name: str, w: torch.Tensor, mode: int, src_c=None, transposed_conv: bool = False) -> torch.Tensor:
+        key = (name, mode)
+        hit = self._pack_cache.get(key)
+        if hit is not None and hit[0] == w._version and hit[1] == w.data_ptr():
+            return hit[2]
+        if transposed_conv:
+            packed = ops.pack_convt_weight(w.detach(), mode)
+        else:
+            packed = ops.pack_conv_weight(w.detach(), src_c if src_c is not None else [w.shape[1]], mode)
+        self._pack_cache[key] = (w._version, w.data_ptr(), packed)
+        return packed
+
+    def _new_grad(self, name: str, like: torch.Tensor) -> torch.Tensor:
+        if self._grad_alloc is not None:
+            return self._grad_alloc(name, tuple(like.shape), like.device)
+        return torch.empty(like.shape, dtype=torch.float32, device=like.device)
+
+    def _done(self, *names: str) -> None:
+        if self._grad_ready is not None:
+            for n in names:
+                self._grad_ready(n)
+
+    # ---------------------------------------------------------------- forward
+    def _conv(self, name, srcs, P, pad, relu=True):
+        w, b = P[name + ".weight"], P[name + ".bias"]
+        return ops.conv_fwd(srcs, w.detach(), b.detach(), pad, relu, impl=self.conv_impl)
+
+    def _block_forward(self, prefix: str, blk: UNetConvBlock, srcs, P, tape):
+        """UNetConvBlock.forward (unet.py:104-106).  Returns (output, post-ReLU activation of the 2nd conv)."""
+        pad = int(self.padding)
+        rec = {"srcs": srcs}
+        names = [f"{prefix}.block.0", f"{prefix}.block.{3 if blk.batch_norm else 2}"]
+        bn_names = [f"{prefix}.block.2", f"{prefix}.block.5"]
+        cur = srcs
+        for i in range(2):
+            a = self._conv(names[i], cur, P, pad)
+            rec[f"a{i}"] = a
+            if blk.batch_norm:
+                bn = blk.bns()[i]
+                g, bt = P[bn_names[i] + ".weight"].detach(), P[bn_names[i] + ".bias"].detach()
+                if self.training or bn.running_mean is None:
+                    o, mean, invstd = ops.bn_fwd_train(a, g, bt, bn.running_mean if self.training else None,
+                                                       bn.running_var if self.training else None,
+                                                       bn.momentum if bn.momentum is not None else 0.1, bn.eps)
+                    if self.training and bn.num_batches_tracked is not None:
+                        bn.num_batches_tracked += 1
+                    rec[f"bn{i}"] = (mean, invstd)
+                else:
+                    o = ops.bn_fwd_eval(a, g, bt, bn.running_mean, bn.running_var, bn.eps)
+                    rec[f"bn{i}"] = None
+            else:
+                o = a
+            rec[f"o{i}"] = o
+            cur = [o]
+        if tape is not None:
+            tape.blocks[prefix] = rec
+        return rec["o1"], rec["a1"]
+
+    def _run_forward(self, x, labels, P, tape):
+        if x.dtype != torch.float32:
+            x = x.float()
+        cur = ops.to_nhwc(x)
+        bridges = []
+        last_act = None
+        for i, down in enumerate(self.down_path):
+            cur, last_act = self._block_forward(f"down_path.{i}", down, [cur], P, tape)
+            if i != self.depth - 1:
+                bridges.append((cur, last_act))
+                pooled, idx8 = ops.maxpool_fwd(cur)  # unet.py:79
+                if tape is not None:
+                    tape.pools.append({"idx8": idx8, "src_shape": cur.shape, "act": last_act})
+                cur = pooled
+        for j, up in enumerate(self.up_path):
+            bridge, _ = bridges[-j - 1]
+            rec = {"x": cur, "x_act": last_act}
+            if self.up_mode == "upconv":
+                w, b = P[f"up_path.{j}.up.weight"].detach(), P[f"up_path.{j}.up.bias"].detach()
+                upv = ops.convt_fwd(cur, w, b, impl=self.conv_impl)
+            else:
+                u = ops.bilinear_fwd(cur)
+                rec["u"] = u
+                upv = self._conv(f"up_path.{j}.up.1", [u], P, 0, relu=False)
+            win, dy, dx = _crop_window(bridge, upv.shape[1], upv.shape[2])
+            rec.update({"crop": (dy, dx), "bridge_shape": bridge.shape, "up_shape": upv.shape})
+            if tape is not None:
+                tape.ups.append(rec)
+            cur, last_act = self._block_forward(f"up_path.{j}.conv_block", up.conv_block, [upv, win], P, tape)
+        hname = "last.0" if self.non_neg else "last"
+        hw, hb = P[hname + ".weight"].detach(), P[hname + ".bias"].detach()
+        hw2 = hw.view(hw.shape[0], hw.shape[1])
+        if tape is not None:
+            tape.head = {"x": cur, "act": last_act}
+        if labels is None:
+            return ops.head_fwd(cur, hw2, hb, self.non_neg)
+        loss, state, _ = ops.head_ce_fwd(cur, hw2, hb, self.non_neg, labels.contiguous())
+        if tape is not None:
+            tape.head["state"] = state
+        return loss
+
+    # ---------------------------------------------------------------- backward
+    def _block_backward(self, prefix: str, blk: UNetConvBlock, tape, P, g, grads, src_dsts, src_masks):
+        """Reverse of _block_forward.  `g` = gradient w.r.t. the block output (already ReLU-masked when there is no
+        BatchNorm).  src_dsts: destination tensors for the gradient of each source (None = not needed)."""
+        rec = tape.blocks.pop(prefix)
+        pad = int(self.padding)
+        names = [f"{prefix}.block.0", f"{prefix}.block.{3 if blk.batch_norm else 2}"]
+        bn_names = [f"{prefix}.block.2", f"{prefix}.block.5"]
+        for i in (1, 0):
+            a = rec[f"a{i}"]
+            if blk.batch_norm:
+                mean, invstd = rec[f"bn{i}"]
+                gam = P[bn_names[i] + ".weight"]
+                dgam = self._new_grad(bn_names[i] + ".weight", gam)
+                dbet = self._new_grad(bn_names[i] + ".bias", gam)
+                dz, _, _ = ops.bn_bwd(a, g, gam.detach(), mean, invstd, True, dx=g, dgamma=dgam, dbeta=dbet)
+                grads[bn_names[i] + ".weight"], grads[bn_names[i] + ".bias"] = dgam, dbet
+            else:
+                dz = g
+            w = P[names[i] + ".weight"]
+            srcs = rec["srcs"] if i == 0 else [rec["o0"]]
+            dw = self._new_grad(names[i] + ".weight", w)
+            db = self._new_grad(names[i] + ".bias", P[names[i] + ".bias"])
+            ops.conv_wgrad(dz, srcs, 3, pad, impl=self.conv_impl, dw=dw, db=db)
+            grads[names[i] + ".weight"], grads[names[i] + ".bias"] = dw, db
+            if i == 1:
+                g = torch.empty_like(rec["o0"])
+                ops.conv_dgrad(dz, w.detach(), pad, [g], [None if blk.batch_norm else rec["a0"]], impl=self.conv_impl)
+            elif src_dsts is not None:
+                ops.conv_dgrad(dz, w.detach(), pad, src_dsts, src_masks, impl=self.conv_impl)
+            self._done(*( [bn_names[i] + ".weight", bn_names[i] + ".bias"] if blk.batch_norm else [] ),
+                       names[i] + ".weight", names[i] + ".bias")
+
+    def _run_backward(self, tape, P, labels, grad_out) -> Dict[str, torch.Tensor]:
+        grads: Dict[str, torch.Tensor] = {}
+        bn = self.batch_norm
+        hname = "last.0" if self.non_neg else "last"
+        hw, hb = P[hname + ".weight"], P[hname + ".bias"]
+        hw2 = hw.detach().view(hw.shape[0], hw.shape[1])
+        hx, hact = tape.head["x"], tape.head["act"]
+        g = torch.empty_like(hx)
+        mask = None if bn else hact
+        if labels is None:
+            _, dw, db = ops.head_bwd(hx, hw2, hb.detach(), self.non_neg, grad_out.float(), dx=g, mask=mask)
+        else:
+            gs = grad_out.detach().reshape(1).float()
+            _, dw, db = ops.head_ce_bwd(hx, hw2, hb.detach(), self.non_neg, labels.contiguous(), tape.head["state"],
+                                        grad_scale=gs, dx=g, mask=mask)
+        dwh = self._new_grad(hname + ".weight", hw)
+        dbh = self._new_grad(hname + ".bias", hb)
+        dwh.copy_(dw.view_as(dwh))
+        dbh.copy_(db)
+        grads[hname + ".weight"], grads[hname + ".bias"] = dwh, dbh
+        self._done(hname + ".weight", hname + ".bias")
+
+        bridge_grads: Dict[int, Tuple[torch.Tensor, Tuple[int, int, int, int]]] = {}
+        # decoder, deepest-first order reversed
+        for j in reversed(range(len(self.up_path))):
+            up = self.up_path[j]
+            rec = tape.ups[j]
+            level = self.depth - 2 - j  # index of the bridge in down_path
+            d_up = torch.empty(rec["up_shape"], dtype=torch.bfloat16, device=g.device)
+            gb = torch.empty(rec["bridge_shape"], dtype=torch.bfloat16, device=g.device)
+            dy, dx = rec["crop"]
+            win = gb[:, dy:dy + d_up.shape[1], dx:dx + d_up.shape[2], :]
+            bridge_grads[level] = (gb, (dy, dx, d_up.shape[1], d_up.shape[2]))
+            self._block_backward(f"up_path.{j}.conv_block", up.conv_block, tape, P, g, grads, [d_up, win], [None, None])
+            xin, xact = rec["x"], rec["x_act"]
+            g = torch.empty_like(xin)
+            xmask = None if bn else xact
+            if self.up_mode == "upconv":
+                wn = f"up_path.{j}.up"
+                w = P[wn + ".weight"]
+                dw = self._new_grad(wn + ".weight", w)
+                db = self._new_grad(wn + ".bias", P[wn + ".bias"])
+                ops.convt_wgrad(xin, d_up, impl=self.conv_impl, dw=dw, db=db)
+                ops.convt_dgrad(d_up, w.detach(), g, mask=xmask, impl=self.conv_impl)
+            else:
+                wn = f"up_path.{j}.up.1"
+                w = P[wn + ".weight"]
+                dw = self._new_grad(wn + ".weight", w)
+                db = self._new_grad(wn + ".bias", P[wn + ".bias"])
+                ops.conv_wgrad(d_up, [rec["u"]], 1, 0, impl=self.conv_impl, dw=dw, db=db)
+                gu = torch.empty_like(rec["u"])
+                ops.conv_dgrad(d_up, w.detach(), 0, [gu], [None], impl=self.conv_impl)
+                ops.bilinear_bwd(gu, g, mask=xmask)
+            grads[wn + ".weight"], grads[wn + ".bias"] = dw, db
+            self._done(wn + ".weight", wn + ".bias")
+            rec.clear()
+        # encoder
+        for i in reversed(range(self.depth)):
+            down = self.down_path[i]
+            if i != self.depth - 1:
+                pool = tape.pools[i]
+                gb, (dy, dx, wh, ww) = bridge_grads.pop(i)
+                add = gb[:, dy:dy + wh, dx:dx + ww, :]
+                ops.maxpool_bwd(g, pool["idx8"], gb, add=add, add_y=dy, add_x=dx, mask=None if bn else pool["act"])
+                g = gb
+            if i == 0:
+                self._block_backward(f"down_path.{i}", down, tape, P, g, grads, None, None)
+            else:
+                prev_pooled_shape = tape.blocks[f"down_path.{i}"]["srcs"][0].shape
+                gp = torch.empty(prev_pooled_shape, dtype=torch.bfloat16, device=g.device)
+                self._block_backward(f"down_path.{i}", down, tape, P, g, grads, [gp], [None])
+                g = gp
+        return grads

@@ -1,0 +1,114 @@
+// Deterministic per-channel reductions over the pixels of NHWC bf16 views (BatchNorm statistics, BatchNorm
+// backward sums, bias gradients).  Pass 1 writes one fp32 partial per block, pass 2 (the caller's finalize
+// kernel) sums the partials in double in a fixed order, so results are run-to-run reproducible.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kReduceMaxBlocks = 4 * kNumSMsB200;
+constexpr int kReduceThreads = 256;
+
+// Functor contract:  template<int VEC> __device__ void operator()(const float (&a)[VEC], const float (&b)[VEC],
+//                                                                  float (&acc)[NV][VEC]) const;
+// `b` is only loaded when HAS_B.
+template <int VEC, int NV, bool HAS_B, class F>
+__global__ void __launch_bounds__(kReduceThreads)
+chan_reduce_kernel(F f, DView a, DView b, int lanes, int tb, long long npix, float* __restrict__ partial) {
+  extern __shared__ float red[];  // [NV*VEC][tb]
+  const int t = threadIdx.x;
+  float acc[NV][VEC];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[v][j] = 0.f;
+
+  if (t < tb) {
+    const int ps = t / lanes, l = t - ps * lanes;
+    const int pb = tb / lanes;
+    const long long hw = (long long)a.h * a.w;
+    for (long long p = (long long)blockIdx.x * pb + ps; p < npix; p += (long long)gridDim.x * pb) {
+      const int n = (int)(p / hw);
+      const int r = (int)(p - n * hw);
+      const int ih = r / a.w, iw = r - ih * a.w;
+      float fa[VEC], fb[VEC];
+      if (VEC == 8) {
+        float t8[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(a.p + a.off(n, ih, iw) + l * 8), t8);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) fa[j] = t8[j];
+        if (HAS_B) {
+          unpack8(*reinterpret_cast<const bf16x8*>(b.p + b.off(n, ih, iw) + l * 8), t8);
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) fb[j] = t8[j];
+        }
+      } else {
+        fa[0] = bf2f(a.p[a.off(n, ih, iw) + l]);
+        if (HAS_B) fb[0] = bf2f(b.p[b.off(n, ih, iw) + l]);
+      }
+      if (!HAS_B) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) fb[j] = 0.f;
+      }
+      f(fa, fb, acc, l * VEC);
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) red[(v * VEC + j) * tb + t] = acc[v][j];
+  }
+  __syncthreads();
+  // thread q sums column (v, channel) over the pixel slots in fixed order
+  const int c = lanes * VEC;
+  for (int q = t; q < NV * c; q += blockDim.x) {
+    const int v = q / c, ch = q - v * c;
+    const int l = ch / VEC, j = ch - l * VEC;
+    float s = 0.f;
+    for (int ps = 0; ps < tb / lanes; ++ps) s += red[(v * VEC + j) * tb + ps * lanes + l];
+    partial[((long long)blockIdx.x * NV + v) * c + ch] = s;
+  }
+}
+
+struct ReducePlan {
+  int vec, lanes, tb, blocks;
+  size_t smem;
+};
+
+// Returns false if the channel count is not supported (c % 8 != 0 and c > 256, or c > 2048).
+inline bool plan_reduce(const b200_view& a, const b200_view* b, int nv, ReducePlan* pl) {
+  const bool al = (reinterpret_cast<uintptr_t>(a.ptr) % 16 == 0) && a.stride_w % 8 == 0 && a.stride_h % 8 == 0 &&
+                  a.stride_n % 8 == 0 &&
+                  (!b || ((reinterpret_cast<uintptr_t>(b->ptr) % 16 == 0) && b->stride_w % 8 == 0 &&
+                          b->stride_h % 8 == 0 && b->stride_n % 8 == 0));
+  pl->vec = (a.c % 8 == 0 && al) ? 8 : 1;
+  pl->lanes = a.c / pl->vec;
+  if (pl->lanes > kReduceThreads) return false;
+  pl->tb = (kReduceThreads / pl->lanes) * pl->lanes;
+  const long long npix = view_pixels(a);
+  const long long pb = pl->tb / pl->lanes;
+  long long blocks = (npix + pb * 8 - 1) / (pb * 8);  // >= 8 pixels per thread slot
+  if (blocks < 1) blocks = 1;
+  if (blocks > kReduceMaxBlocks) blocks = kReduceMaxBlocks;
+  pl->blocks = (int)blocks;
+  pl->smem = (size_t)nv * pl->vec * pl->tb * sizeof(float);
+  return true;
+}
+
+inline size_t reduce_workspace_bytes(int c, int nv) { return (size_t)kReduceMaxBlocks * nv * c * sizeof(float); }
+
+template <int NV, bool HAS_B, class F>
+inline int launch_chan_reduce(F f, const b200_view& a, const b200_view* b, float* partial, ReducePlan* pl,
+                              cudaStream_t st) {
+  if (!plan_reduce(a, b, NV, pl)) return fail(-1, "channel reduction: unsupported channel count %d", a.c);
+  DView da = dview(a), db = b ? dview(*b) : da;
+  const long long npix = view_pixels(a);
+  if (pl->vec == 8)
+    chan_reduce_kernel<8, NV, HAS_B, F><<<pl->blocks, kReduceThreads, pl->smem, st>>>(f, da, db, pl->lanes, pl->tb,
+                                                                                     npix, partial);
+  else
+    chan_reduce_kernel<1, NV, HAS_B, F><<<pl->blocks, kReduceThreads, pl->smem, st>>>(f, da, db, pl->lanes, pl->tb,
+                                                                                     npix, partial);
+  return check_launch("chan_reduce");
+}
+
+}  // namespace b200

@@ -1,0 +1,87 @@
+// Shared host/device helpers of libb200unet: error reporting, view validation, small device utilities.
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/b200unet.h"
+
+namespace b200 {
+
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------ errors (thread-local message)
+char* err_buf();
+int fail(int code, const char* fmt, ...);
+int check_launch(const char* what);
+
+#define B200_REQUIRE(cond, ...)                     \
+  do {                                              \
+    if (!(cond)) return ::b200::fail(-1, __VA_ARGS__); \
+  } while (0)
+
+inline bool view_ok(const b200_view* v) {
+  return v && v->ptr && v->n > 0 && v->h > 0 && v->w > 0 && v->c > 0 && v->stride_w >= v->c;
+}
+inline bool same_extent(const b200_view& a, const b200_view& b) {
+  return a.n == b.n && a.h == b.h && a.w == b.w && a.c == b.c;
+}
+inline int64_t view_pixels(const b200_view& v) { return (int64_t)v.n * v.h * v.w; }
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+constexpr int kNumSMsB200 = 148;
+
+// ------------------------------------------------------------------ device view (POD copy usable in kernels)
+struct DView {
+  bf16* p;
+  int n, h, w, c;
+  long long sn, sh, sw;
+  __host__ __device__ long long off(int in, int ih, int iw) const { return in * sn + ih * sh + iw * sw; }
+};
+inline DView dview(const b200_view& v) {
+  return DView{reinterpret_cast<bf16*>(v.ptr), v.n, v.h, v.w, v.c, v.stride_n, v.stride_h, v.stride_w};
+}
+
+// 16-byte vector path is usable on this view
+inline bool vec8_ok(const b200_view& v) {
+  return v.c % 8 == 0 && reinterpret_cast<uintptr_t>(v.ptr) % 16 == 0 && v.stride_w % 8 == 0 && v.stride_h % 8 == 0 &&
+         v.stride_n % 8 == 0;
+}
+inline int stream_grid(long long total) {
+  long long g = (total + 255) / 256;
+  const long long cap = (long long)kNumSMsB200 * 8;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+__device__ __forceinline__ float bf2f(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ bf16 f2bf(float v) { return __float2bfloat16_rn(v); }
+
+// 8 bf16 <-> 8 floats through one 16-byte access
+struct __align__(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+__device__ __forceinline__ void unpack8(const bf16x8& p, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(p.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
+  bf16x8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace b200

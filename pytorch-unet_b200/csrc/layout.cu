@@ -1,0 +1,229 @@
+// Boundary transforms: NCHW fp32 <-> NHWC bf16, weight packing into GEMM operand layouts, ReLU masking,
+// per-channel sums (bias gradients).
+#include "chan_reduce.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------ NCHW fp32 -> NHWC bf16 (unet.py:73 input)
+// One thread per pixel; reads are coalesced along w for every channel plane, writes are C contiguous bf16.
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, DView dst) {
+  const long long hw = (long long)dst.h * dst.w;
+  const long long total = hw * dst.n;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(p / hw);
+    const long long r = p - n * hw;
+    const int ih = (int)(r / dst.w), iw = (int)(r - (long long)ih * dst.w);
+    bf16* o = dst.p + dst.off(n, ih, iw);
+    const float* s = src + (long long)n * dst.c * hw + r;
+    for (int c = 0; c < dst.c; ++c) o[c] = f2bf(s[c * hw]);
+  }
+}
+
+// Tiled transpose for wide tensors: block handles 32 pixels x 32 channels through shared memory.
+__global__ void nhwc_to_nchw_kernel(DView src, float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const long long hw = (long long)src.h * src.w;
+  const long long total = hw * src.n;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  {
+    const long long p = p0 + threadIdx.y;
+    const int c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (p < total && c < src.c) {
+      const int n = (int)(p / hw);
+      const long long r = p - n * hw;
+      const int ih = (int)(r / src.w), iw = (int)(r - (long long)ih * src.w);
+      v = bf2f(src.p[src.off(n, ih, iw) + c]);
+    }
+    tile[threadIdx.y][threadIdx.x] = v;
+  }
+  __syncthreads();
+  {
+    const long long p = p0 + threadIdx.x;
+    const int c = c0 + threadIdx.y;
+    if (p < total && c < src.c) {
+      const int n = (int)(p / hw);
+      const long long r = p - n * hw;
+      dst[((long long)n * src.c + c) * hw + r] = tile[threadIdx.x][threadIdx.y];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ weight packing
+// conv fprop: out[o][tap][kpad]; source i occupies columns [koff_i, koff_i + src_c[i]) of kpad, zero elsewhere.
+__global__ void pack_conv_fprop_kernel(const float* __restrict__ w, bf16* __restrict__ out, int cout, int cin_total,
+                                       int taps, int kpad, int c0, int c0pad) {
+  const long long total = (long long)cout * taps * kpad;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(e % kpad);
+    const int tap = (int)((e / kpad) % taps);
+    const int o = (int)(e / ((long long)kpad * taps));
+    int c = -1;
+    if (k < c0pad) {
+      if (k < c0) c = k;
+    } else {
+      const int k1 = k - c0pad;
+      if (k1 < cin_total - c0) c = c0 + k1;
+    }
+    out[e] = f2bf(c >= 0 ? w[((long long)o * cin_total + c) * taps + tap] : 0.f);
+  }
+}
+
+// conv dgrad: out[c][tap'][opad] = w[o][c][taps-1-tap'] (spatial flip), zero for o >= cout.
+__global__ void pack_conv_dgrad_kernel(const float* __restrict__ w, bf16* __restrict__ out, int cout, int cin_total,
+                                       int taps, int opad) {
+  const long long total = (long long)cin_total * taps * opad;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(e % opad);
+    const int tap = (int)((e / opad) % taps);
+    const int c = (int)(e / ((long long)opad * taps));
+    out[e] = f2bf(o < cout ? w[((long long)o * cin_total + c) * taps + (taps - 1 - tap)] : 0.f);
+  }
+}
+
+// convT fwd: out[(ab*cout + o)][cpad] = w[c][o][ab];  convT dgrad: out[c][ab][opad] = w[c][o][ab]
+__global__ void pack_convt_kernel(const float* __restrict__ w, bf16* __restrict__ out, int cin, int cout, int mode,
+                                  int kp) {
+  if (mode == 0) {
+    const long long total = (long long)4 * cout * kp;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+      const int c = (int)(e % kp);
+      const int row = (int)(e / kp);
+      const int ab = row / cout, o = row - ab * cout;
+      out[e] = f2bf(c < cin ? w[((long long)c * cout + o) * 4 + ab] : 0.f);
+    }
+  } else {
+    const long long total = (long long)cin * 4 * kp;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+      const int o = (int)(e % kp);
+      const int ab = (int)((e / kp) % 4);
+      const int c = (int)(e / ((long long)kp * 4));
+      out[e] = f2bf(o < cout ? w[((long long)c * cout + o) * 4 + ab] : 0.f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ y = mask > 0 ? x : 0
+__global__ void relu_mask_kernel(DView x, DView m, DView y) {
+  const long long total = (long long)x.n * x.h * x.w * x.c;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % x.c);
+    long long p = e / x.c;
+    const int iw = (int)(p % x.w);
+    p /= x.w;
+    const int ih = (int)(p % x.h);
+    const int n = (int)(p / x.h);
+    const float mv = bf2f(m.p[m.off(n, ih, iw) + c]);
+    y.p[y.off(n, ih, iw) + c] = mv > 0.f ? x.p[x.off(n, ih, iw) + c] : f2bf(0.f);
+  }
+}
+
+struct SumF {
+  template <int VEC>
+  __device__ void operator()(const float (&a)[VEC], const float (&)[VEC], float (&acc)[1][VEC], int) const {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[0][j] += a[j];
+  }
+};
+
+__global__ void finalize_sum_kernel(const float* __restrict__ partial, int blocks, int c, float* __restrict__ out) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  double s = 0.0;
+  for (int b = 0; b < blocks; ++b) s += (double)partial[(long long)b * c + ch];
+  out[ch] = (float)s;
+}
+
+inline int grid_for(long long total, int threads) {
+  long long g = (total + threads - 1) / threads;
+  const long long cap = (long long)kNumSMsB200 * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200unet_nchw_f32_to_nhwc_bf16(const float* src, const b200_view* dst, void* stream) {
+  B200_REQUIRE(src && view_ok(dst), "nchw_to_nhwc: bad arguments");
+  nchw_to_nhwc_kernel<<<grid_for(view_pixels(*dst), 256), 256, 0, as_stream(stream)>>>(src, dview(*dst));
+  return check_launch("nchw_to_nhwc");
+}
+
+int b200unet_nhwc_bf16_to_nchw_f32(const b200_view* src, float* dst, void* stream) {
+  B200_REQUIRE(dst && view_ok(src), "nhwc_to_nchw: bad arguments");
+  const long long total = view_pixels(*src);
+  dim3 grid((unsigned)((total + 31) / 32), (unsigned)((src->c + 31) / 32));
+  nhwc_to_nchw_kernel<<<grid, dim3(32, 32), 0, as_stream(stream)>>>(dview(*src), dst);
+  return check_launch("nhwc_to_nchw");
+}
+
+static int conv_kpad(int num_src, const int* src_c) {
+  int k = 0;
+  for (int i = 0; i < num_src; ++i) k += (src_c[i] + 63) / 64 * 64;
+  return k;
+}
+
+size_t b200unet_pack_conv_weight_bytes(int cout, int num_src, const int* src_c, int taps, int mode) {
+  if (!src_c || num_src < 1 || num_src > 2) return 0;
+  int cin = 0;
+  for (int i = 0; i < num_src; ++i) cin += src_c[i];
+  if (mode == 0) return (size_t)cout * taps * conv_kpad(num_src, src_c) * 2;
+  return (size_t)cin * taps * ((cout + 63) / 64 * 64) * 2;
+}
+
+int b200unet_pack_conv_weight(const float* w, int cout, int num_src, const int* src_c, int taps, int mode, void* out,
+                              void* stream) {
+  B200_REQUIRE(w && out && src_c && num_src >= 1 && num_src <= 2 && (taps == 1 || taps == 9) && cout > 0,
+               "pack_conv_weight: bad arguments");
+  int cin = 0;
+  for (int i = 0; i < num_src; ++i) cin += src_c[i];
+  if (mode == 0) {
+    const int kpad = conv_kpad(num_src, src_c);
+    const int c0 = src_c[0], c0pad = (c0 + 63) / 64 * 64;
+    const long long total = (long long)cout * taps * kpad;
+    pack_conv_fprop_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(w, (bf16*)out, cout, cin, taps, kpad,
+                                                                                c0, c0pad);
+  } else {
+    const int opad = (cout + 63) / 64 * 64;
+    const long long total = (long long)cin * taps * opad;
+    pack_conv_dgrad_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(w, (bf16*)out, cout, cin, taps, opad);
+  }
+  return check_launch("pack_conv_weight");
+}
+
+size_t b200unet_pack_convt_weight_bytes(int cin, int cout, int mode) {
+  if (mode == 0) return (size_t)4 * cout * ((cin + 63) / 64 * 64) * 2;
+  return (size_t)cin * 4 * ((cout + 63) / 64 * 64) * 2;
+}
+
+int b200unet_pack_convt_weight(const float* w, int cin, int cout, int mode, void* out, void* stream) {
+  B200_REQUIRE(w && out && cin > 0 && cout > 0, "pack_convt_weight: bad arguments");
+  const int kp = mode == 0 ? (cin + 63) / 64 * 64 : (cout + 63) / 64 * 64;
+  const long long total = mode == 0 ? (long long)4 * cout * kp : (long long)cin * 4 * kp;
+  pack_convt_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(w, (bf16*)out, cin, cout, mode, kp);
+  return check_launch("pack_convt_weight");
+}
+
+int b200unet_relu_mask(const b200_view* x, const void* mask, const b200_view* y, void* stream) {
+  B200_REQUIRE(view_ok(x) && view_ok(y) && mask && same_extent(*x, *y), "relu_mask: bad arguments");
+  DView m = dview(*y);
+  m.p = (bf16*)mask;
+  const long long total = view_pixels(*x) * x->c;
+  relu_mask_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(dview(*x), m, dview(*y));
+  return check_launch("relu_mask");
+}
+
+int b200unet_channel_sum(const b200_view* dz, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  B200_REQUIRE(view_ok(dz) && out && workspace, "channel_sum: bad arguments");
+  B200_REQUIRE(workspace_bytes >= reduce_workspace_bytes(dz->c, 1), "channel_sum: workspace too small");
+  ReducePlan pl;
+  int r = launch_chan_reduce<1, false>(SumF(), *dz, nullptr, (float*)workspace, &pl, as_stream(stream));
+  if (r) return r;
+  finalize_sum_kernel<<<(dz->c + 127) / 128, 128, 0, as_stream(stream)>>>((const float*)workspace, pl.blocks, dz->c, out);
+  return check_launch("channel_sum finalize");
+}
+}

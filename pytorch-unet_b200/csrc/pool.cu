@@ -1,0 +1,205 @@
+// F.max_pool2d(x, 2) forward with arg-max codes, and its backward fused with the skip-connection gradient add
+// and the producer's ReLU mask (reference: unet.py:79 forward; unet.py:152-163 + autograd for the backward).
+// HBM-bound: one thread moves 8 channels (16 B) of one 2x2 window; NHWC makes every access a full 16-byte
+// vector and consecutive threads cover consecutive channels, then consecutive pixels -> fully coalesced.
+#include "common.cuh"
+
+namespace b200 {
+
+// ATen rule (aten/src/ATen/native/cpu/MaxPoolKernel.cpp semantics): scan (0,0),(0,1),(1,0),(1,1); replace when
+// val > max or val is NaN.  Start: max = -inf, index = first element.
+__device__ __forceinline__ void pool_scan(float v, int code, float& best, int& arg) {
+  if (v > best || v != v) {
+    best = v;
+    arg = code;
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+maxpool_fwd_kernel(DView x, DView y, uint8_t* __restrict__ idx8, long long* __restrict__ idx64) {
+  const int lanes = y.c / VEC;
+  const long long total = (long long)y.n * y.h * y.w * lanes;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int l = (int)(e % lanes);
+    long long p = e / lanes;
+    const int ow = (int)(p % y.w);
+    p /= y.w;
+    const int oh = (int)(p % y.h);
+    const int n = (int)(p / y.h);
+    float v[4][VEC];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const bf16* s = x.p + x.off(n, 2 * oh + a, 2 * ow + b) + l * VEC;
+        if (VEC == 8) {
+          float t[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(s), t);
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) v[a * 2 + b][j] = t[j];
+        } else {
+          v[a * 2 + b][0] = bf2f(s[0]);
+        }
+      }
+    float best[VEC];
+    int arg[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      best[j] = -INFINITY;
+      arg[j] = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) pool_scan(v[k][j], k, best[j], arg[j]);
+    }
+    const long long opix = ((long long)n * y.h + oh) * y.w + ow;
+    bf16* o = y.p + y.off(n, oh, ow) + l * VEC;
+    if (VEC == 8) {
+      float t[8];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) t[j] = best[j];
+      *reinterpret_cast<bf16x8*>(o) = pack8(t);
+      uint2 codes;
+      codes.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+      codes.y = arg[4 % VEC] | (arg[5 % VEC] << 8) | (arg[6 % VEC] << 16) | (arg[7 % VEC] << 24);
+      *reinterpret_cast<uint2*>(idx8 + opix * y.c + l * 8) = codes;
+    } else {
+      o[0] = f2bf(best[0]);
+      idx8[opix * y.c + l] = (uint8_t)arg[0];
+    }
+    if (idx64) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j)
+        idx64[opix * y.c + l * VEC + j] = (long long)(2 * oh + (arg[j] >> 1)) * x.w + (2 * ow + (arg[j] & 1));
+    }
+  }
+}
+
+// One thread per 2x2 window position of dx (windows also cover a trailing odd row / column, where only the
+// skip-gradient term exists).
+template <int VEC>
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(DView dy, const uint8_t* __restrict__ idx8, DView dx, DView add, int has_add, int add_y, int add_x,
+                   const bf16* __restrict__ mask) {
+  const int lanes = dx.c / VEC;
+  const int wh = (dx.h + 1) / 2, ww = (dx.w + 1) / 2;
+  const long long total = (long long)dx.n * wh * ww * lanes;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int l = (int)(e % lanes);
+    long long p = e / lanes;
+    const int ow = (int)(p % ww);
+    p /= ww;
+    const int oh = (int)(p % wh);
+    const int n = (int)(p / wh);
+    const bool win = oh < dy.h && ow < dy.w;
+    float g[VEC];
+    int code[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      g[j] = 0.f;
+      code[j] = -1;
+    }
+    if (win) {
+      const long long opix = ((long long)n * dy.h + oh) * dy.w + ow;
+      const bf16* s = dy.p + dy.off(n, oh, ow) + l * VEC;
+      if (VEC == 8) {
+        float t[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(s), t);
+        const uint2 cw = *reinterpret_cast<const uint2*>(idx8 + opix * dy.c + l * 8);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          g[j] = t[j];
+          code[j] = ((j < 4 ? cw.x : cw.y) >> (8 * (j & 3))) & 0xff;
+        }
+      } else {
+        g[0] = bf2f(s[0]);
+        code[0] = idx8[opix * dy.c + l];
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int ih = 2 * oh + a, iw = 2 * ow + b;
+        if (ih >= dx.h || iw >= dx.w) continue;
+        float r[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) r[j] = (code[j] == a * 2 + b) ? g[j] : 0.f;
+        const int ay = ih - add_y, ax = iw - add_x;
+        if (has_add && ay >= 0 && ay < add.h && ax >= 0 && ax < add.w) {
+          const bf16* s = add.p + add.off(n, ay, ax) + l * VEC;
+          if (VEC == 8) {
+            float t[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(s), t);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) r[j] += t[j];
+          } else {
+            r[0] += bf2f(s[0]);
+          }
+        }
+        const long long o = dx.off(n, ih, iw) + l * VEC;
+        if (mask) {
+          if (VEC == 8) {
+            float t[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(mask + o), t);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) r[j] = t[j] > 0.f ? r[j] : 0.f;
+          } else {
+            r[0] = bf2f(mask[o]) > 0.f ? r[0] : 0.f;
+          }
+        }
+        if (VEC == 8) {
+          float t[8];
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) t[j] = r[j];
+          *reinterpret_cast<bf16x8*>(dx.p + o) = pack8(t);
+        } else {
+          dx.p[o] = f2bf(r[0]);
+        }
+      }
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200unet_maxpool2x2_fwd(const b200_view* x, const b200_view* y, uint8_t* idx8, int64_t* idx64, void* stream) {
+  B200_REQUIRE(view_ok(x) && view_ok(y) && idx8, "maxpool_fwd: bad arguments");
+  B200_REQUIRE(y->n == x->n && y->c == x->c && y->h == x->h / 2 && y->w == x->w / 2,
+               "maxpool_fwd: output extent must be floor(input/2)");
+  const bool v8 = vec8_ok(*x) && vec8_ok(*y) && reinterpret_cast<uintptr_t>(idx8) % 8 == 0;
+  const long long total = view_pixels(*y) * (v8 ? y->c / 8 : y->c);
+  if (v8)
+    maxpool_fwd_kernel<8><<<stream_grid(total), 256, 0, as_stream(stream)>>>(dview(*x), dview(*y), idx8,
+                                                                            (long long*)idx64);
+  else
+    maxpool_fwd_kernel<1><<<stream_grid(total), 256, 0, as_stream(stream)>>>(dview(*x), dview(*y), idx8,
+                                                                            (long long*)idx64);
+  return check_launch("maxpool_fwd");
+}
+
+int b200unet_maxpool2x2_bwd(const b200_view* dy, const uint8_t* idx8, const b200_view* dx, const b200_view* add,
+                            int add_y, int add_x, const void* mask, void* stream) {
+  B200_REQUIRE(view_ok(dy) && view_ok(dx) && idx8, "maxpool_bwd: bad arguments");
+  B200_REQUIRE(dy->n == dx->n && dy->c == dx->c && dy->h == dx->h / 2 && dy->w == dx->w / 2,
+               "maxpool_bwd: dy extent must be floor(dx/2)");
+  if (add) {
+    B200_REQUIRE(view_ok(add) && add->n == dx->n && add->c == dx->c && add_y >= 0 && add_x >= 0 &&
+                     add_y + add->h <= dx->h && add_x + add->w <= dx->w,
+                 "maxpool_bwd: skip-gradient window outside dx");
+  }
+  const bool v8 = vec8_ok(*dy) && vec8_ok(*dx) && (!add || vec8_ok(*add)) &&
+                  reinterpret_cast<uintptr_t>(idx8) % 8 == 0 && reinterpret_cast<uintptr_t>(mask) % 16 == 0;
+  const long long total = (long long)dx->n * ((dx->h + 1) / 2) * ((dx->w + 1) / 2) * (v8 ? dx->c / 8 : dx->c);
+  DView dadd = add ? dview(*add) : dview(*dx);
+  if (v8)
+    maxpool_bwd_kernel<8><<<stream_grid(total), 256, 0, as_stream(stream)>>>(dview(*dy), idx8, dview(*dx), dadd,
+                                                                            add ? 1 : 0, add_y, add_x, (const bf16*)mask);
+  else
+    maxpool_bwd_kernel<1><<<stream_grid(total), 256, 0, as_stream(stream)>>>(dview(*dy), idx8, dview(*dx), dadd,
+                                                                            add ? 1 : 0, add_y, add_x, (const bf16*)mask);
+  return check_launch("maxpool_bwd");
+}
+}
