@@ -126,17 +126,39 @@ def init_params(spec: UNetSpec, seed: int = 0) -> Dict[str, torch.Tensor]:
 
 
 # --------------------------------------------------------------------------- forward
+class _RoundBF16(torch.autograd.Function):
+    """Storage-precision emulation for the `act_bf16` mode: value rounded to bf16 in forward, gradient in backward."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(torch.float32)
+
+
+_ACT_BF16 = False
+
+
+def _q(x):
+    """Identity in the fp32 oracle; bf16 storage rounding when the product's activation precision is emulated
+    (used only to separate "precision" from "logic" differences in the parity tests)."""
+    return _RoundBF16.apply(x) if _ACT_BF16 else x
+
+
 def _conv_block(sd, prefix: str, x, spec: UNetSpec, training: bool, new_stats: Optional[dict]):
     # unet.py:92-100: Conv2d(3x3, padding=int(padding)) -> ReLU -> [BatchNorm2d], twice.
     convs, bns = ((0, 3), (2, 5)) if spec.batch_norm else ((0, 2), (None, None))
     for ci, bi in zip(convs, bns):
         x = F.conv2d(x, sd[f"{prefix}.block.{ci}.weight"], sd[f"{prefix}.block.{ci}.bias"], padding=int(spec.padding))
-        x = F.relu(x)
+        x = _q(F.relu(x))
         if spec.batch_norm:
             name = f"{prefix}.block.{bi}"
             rm = sd[name + ".running_mean"].clone()
             rv = sd[name + ".running_var"].clone()
             x = F.batch_norm(x, rm, rv, sd[name + ".weight"], sd[name + ".bias"], training=training, momentum=0.1, eps=1e-5)
+            x = _q(x)
             if new_stats is not None and training:
                 new_stats[name + ".running_mean"] = rm
                 new_stats[name + ".running_var"] = rv
@@ -149,8 +171,19 @@ def center_crop_offsets(bridge_hw: Tuple[int, int], target_hw: Tuple[int, int]) 
 
 
 def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, spec: UNetSpec, training: bool = True,
-            new_stats: Optional[dict] = None, taps: Optional[dict] = None) -> torch.Tensor:
-    """Logits N x n_classes x H' x W' (unet.py:73-84).  `taps`, if given, collects intermediate tensors."""
+            new_stats: Optional[dict] = None, taps: Optional[dict] = None, act_bf16: bool = False) -> torch.Tensor:
+    """Logits N x n_classes x H' x W' (unet.py:73-84).  `taps`, if given, collects intermediate tensors.
+    act_bf16=True rounds every stored activation (and its gradient) to bf16 like the CUDA path does."""
+    global _ACT_BF16
+    prev, _ACT_BF16 = _ACT_BF16, act_bf16
+    try:
+        return _forward(sd, x, spec, training, new_stats, taps)
+    finally:
+        _ACT_BF16 = prev
+
+
+def _forward(sd, x, spec, training, new_stats, taps):
+    x = _q(x)
     bridges = []
     for i in range(spec.depth):
         x = _conv_block(sd, f"down_path.{i}", x, spec, training, new_stats)
@@ -162,10 +195,10 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, spec: UNetSpec, traini
     for j in range(spec.depth - 1):
         bridge = bridges[-j - 1]
         if spec.up_mode == "upconv":  # unet.py:143 / 173
-            up = F.conv_transpose2d(x, sd[f"up_path.{j}.up.weight"], sd[f"up_path.{j}.up.bias"], stride=2)
+            up = _q(F.conv_transpose2d(x, sd[f"up_path.{j}.up.weight"], sd[f"up_path.{j}.up.bias"], stride=2))
         else:  # unet.py:145-148 / 175-178
-            up = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
-            up = F.conv2d(up, sd[f"up_path.{j}.up.1.weight"], sd[f"up_path.{j}.up.1.bias"])
+            up = _q(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False))
+            up = _q(F.conv2d(up, sd[f"up_path.{j}.up.1.weight"], sd[f"up_path.{j}.up.1.bias"]))
         dy, dx = center_crop_offsets(bridge.shape[2:], up.shape[2:])
         crop = bridge[:, :, dy:dy + up.shape[2], dx:dx + up.shape[3]]
         x = torch.cat([up, crop], 1)  # unet.py:163 — up first, bridge second
@@ -180,15 +213,20 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, spec: UNetSpec, traini
 
 
 def loss_and_grads(sd: Dict[str, torch.Tensor], x: torch.Tensor, y: torch.Tensor, spec: UNetSpec,
-                   training: bool = True):
+                   training: bool = True, act_bf16: bool = False):
     """README.md:57-62 training step up to backward(): returns (logits, loss, {param: grad}, new BN stats)."""
     shapes = param_shapes(spec)
     leaves = {k: (v.detach().clone().requires_grad_(True) if k in shapes else v) for k, v in sd.items()}
     new_stats: dict = {}
-    logits = forward(leaves, x, spec, training=training, new_stats=new_stats)
-    loss = F.cross_entropy(logits, y)
-    names = list(shapes.keys())
-    grads = torch.autograd.grad(loss, [leaves[k] for k in names])
+    global _ACT_BF16
+    prev, _ACT_BF16 = _ACT_BF16, act_bf16  # must also cover the backward pass
+    try:
+        logits = _forward(leaves, x, spec, training, new_stats, None)
+        loss = F.cross_entropy(logits, y)
+        names = list(shapes.keys())
+        grads = torch.autograd.grad(loss, [leaves[k] for k in names])
+    finally:
+        _ACT_BF16 = prev
     return logits.detach(), loss.detach(), dict(zip(names, grads)), new_stats
 
 

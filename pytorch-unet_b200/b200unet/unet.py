@@ -98,7 +98,7 @@ class _UNetFunction(torch.autograd.Function):
     def forward(ctx, model: "UNet", x: torch.Tensor, labels: Optional[torch.Tensor], *params: torch.Tensor):
         names = model._param_names
         P = dict(zip(names, params))
-        keep = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        keep = any(ctx.needs_input_grad[3:])  # False under no_grad / frozen parameters
         tape = _Tape() if keep else None
         out = model._run_forward(x, labels, P, tape)
         ctx.model, ctx.tape, ctx.P, ctx.labels = model, tape, P, labels

@@ -21,3 +21,12 @@ def lib_built():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod.build()
+
+
+@pytest.fixture(autouse=True, scope="session")
+def _strict_fp32_reference():
+    """torch's own CUDA convolutions default to TF32: the per-op oracles must be true fp32."""
+    import torch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
