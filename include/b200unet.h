@@ -147,6 +147,9 @@ int b200unet_convt_wgrad(const b200_convt_wgrad_params* p, void* workspace, size
 int b200unet_conv_fwd_impl(const b200_conv_fwd_params* p);
 int b200unet_conv_dgrad_impl(const b200_conv_dgrad_params* p);
 int b200unet_conv_wgrad_impl(const b200_conv_wgrad_params* p);
+int b200unet_convt_fwd_impl(const b200_convt_fwd_params* p);
+int b200unet_convt_dgrad_impl(const b200_convt_dgrad_params* p);
+int b200unet_convt_wgrad_impl(const b200_convt_wgrad_params* p);
 
 /* ---- weight packing (fp32 state_dict layout -> bf16 GEMM operand layout)
  * conv: w [cout][cin_total][k][k]; src_c[i] = channels of source i (cin_total = sum).

@@ -77,6 +77,9 @@ SIGNATURES = {
     "b200unet_conv_fwd_impl": (_I, [C.POINTER(ConvFwdParams)]),
     "b200unet_conv_dgrad_impl": (_I, [C.POINTER(ConvDgradParams)]),
     "b200unet_conv_wgrad_impl": (_I, [C.POINTER(ConvWgradParams)]),
+    "b200unet_convt_fwd_impl": (_I, [C.POINTER(ConvTFwdParams)]),
+    "b200unet_convt_dgrad_impl": (_I, [C.POINTER(ConvTDgradParams)]),
+    "b200unet_convt_wgrad_impl": (_I, [C.POINTER(ConvTWgradParams)]),
     "b200unet_pack_conv_weight_bytes": (_SZ, [_I, _I, C.POINTER(C.c_int), _I, _I]),
     "b200unet_pack_conv_weight": (_I, [_P, _I, _I, C.POINTER(C.c_int), _I, _I, _P, _P]),
     "b200unet_pack_convt_weight_bytes": (_SZ, [_I, _I, _I]),

@@ -158,7 +158,10 @@ def convt_fwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], w_
     p = ConvTFwdParams()
     p.x, p.y = view(x), view(out)
     p.w_f32, p.bias, p.impl = w.data_ptr(), ptr(bias), impl
-    p.w_packed = ptr(w_packed)
+    if impl != IMPL_DIRECT and lib.b200unet_convt_fwd_impl(C.byref(p)) == IMPL_UMMA:
+        if w_packed is None:
+            w_packed = pack_convt_weight(w, 0)
+        p.w_packed = w_packed.data_ptr()
     check(lib.b200unet_convt_fwd(C.byref(p), stream_ptr()), "convt_fwd")
     return out
 
@@ -169,7 +172,10 @@ def convt_dgrad(dy: torch.Tensor, w: torch.Tensor, dx: torch.Tensor, mask: Optio
     p = ConvTDgradParams()
     p.dy, p.dx = view(dy), view(dx)
     p.w_f32, p.mask, p.impl = w.data_ptr(), ptr(mask), impl
-    p.w_packed = ptr(w_packed)
+    if impl != IMPL_DIRECT and lib.b200unet_convt_dgrad_impl(C.byref(p)) == IMPL_UMMA:
+        if w_packed is None:
+            w_packed = pack_convt_weight(w, 1)
+        p.w_packed = w_packed.data_ptr()
     check(lib.b200unet_convt_dgrad(C.byref(p), stream_ptr()), "convt_dgrad")
 
 

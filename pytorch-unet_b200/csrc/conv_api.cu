@@ -86,6 +86,19 @@ int b200unet_conv_wgrad_impl(const b200_conv_wgrad_params* p) {
   return umma_conv_wgrad_ok(p) ? B200_IMPL_UMMA : B200_IMPL_DIRECT;
 }
 
+int b200unet_convt_fwd_impl(const b200_convt_fwd_params* p) {
+  if (!p || !view_ok(&p->x) || !view_ok(&p->y)) return -1;
+  return umma_convt_fwd_ok(p) ? B200_IMPL_UMMA : B200_IMPL_DIRECT;
+}
+int b200unet_convt_dgrad_impl(const b200_convt_dgrad_params* p) {
+  if (!p || !view_ok(&p->dx) || !view_ok(&p->dy)) return -1;
+  return umma_convt_dgrad_ok(p) ? B200_IMPL_UMMA : B200_IMPL_DIRECT;
+}
+int b200unet_convt_wgrad_impl(const b200_convt_wgrad_params* p) {
+  if (!p || !view_ok(&p->x) || !view_ok(&p->dy)) return -1;
+  return umma_convt_wgrad_ok(p) ? B200_IMPL_UMMA : B200_IMPL_DIRECT;
+}
+
 int b200unet_conv_fwd(const b200_conv_fwd_params* p, void* stream) {
   int r = check_conv_fwd(p), impl;
   if (r) return r;

@@ -1,18 +1,596 @@
-// tcgen05 path (placeholder until the kernels land): reports every shape as unsupported.
+// tcgen05 implicit-GEMM kernel for the convolution family (forward and backward-data):
+//   conv 3x3 / 1x1 forward (+bias, ReLU, two concatenated sources = folded crop + concat)   unet.py:92-98, 152-163
+//   conv 3x3 / 1x1 backward-data (+ReLU mask of the producer, two destinations)             autograd of the above
+//   ConvTranspose2d(2, 2) forward (GEMM with N = 4*Cout + pixel-shuffle store)              unet.py:143, 173
+//   ConvTranspose2d(2, 2) backward-data (GEMM with K = 4*Cout over four stride-2 sub-lattices)
+//
+// GEMM view: D[pixels, Cout] = sum over (source, 64-channel chunk, filter tap) A[pixels, 64] * B[Cout, 64]^T.
+//
+// A operand ("haloed tile"): one TMA box {64 channels, P columns, TH+2 rows} of the NHWC activation is loaded ONCE
+// per 64-channel chunk into SWIZZLE_128B shared memory; its rows are the pixels of the haloed tile in row-major
+// order with pitch P.  The operand of filter tap (r, s) for M-block m is the same buffer read through a UMMA
+// descriptor whose start address is advanced by (m*128 + r*P + s) 128-byte rows: output position q = y*P + x reads
+// row q + r*P + s = (y+r)*P + (x+s).  Positions with x >= P-2 are wasted MMA rows (2 of P) and are discarded by
+// the epilogue.  So the activation tile moves L2 -> SMEM once, not nine times, and zero padding / image borders
+// come from TMA out-of-bounds fill.  (experiments/umma_probe.cu verified on B200 that row-shifted descriptor
+// starts inside a 1024-byte-aligned SWIZZLE_128B buffer are addressed correctly with base_offset = 0.)
+//
+// B operand: packed weights [Cout][tap][kpad] (K-major), one TMA box {64, BN} per (tap, chunk).
+//
+// Warp roles (7 warps, 1 CTA / SM, persistent over tiles): 0 = A producer, 1 = B producer, 2 = TMEM allocator +
+// single-thread tcgen05.mma issuer, 3..6 = epilogue (tcgen05.ld -> bias / ReLU / mask -> bf16 -> global).
+// Accumulators: MB x BN fp32 columns in TMEM, double-buffered when 2*MB*BN <= 512 so the epilogue of tile i overlaps
+// the MMAs of tile i+1.
 #include "conv_impl.h"
+#include "ptx.cuh"
+#include "tmap.h"
+
 namespace b200 {
-bool umma_conv_fwd_ok(const b200_conv_fwd_params*) { return false; }
-bool umma_conv_dgrad_ok(const b200_conv_dgrad_params*) { return false; }
-bool umma_conv_wgrad_ok(const b200_conv_wgrad_params*) { return false; }
-bool umma_convt_fwd_ok(const b200_convt_fwd_params*) { return false; }
-bool umma_convt_dgrad_ok(const b200_convt_dgrad_params*) { return false; }
-bool umma_convt_wgrad_ok(const b200_convt_wgrad_params*) { return false; }
-int umma_conv_fwd(const b200_conv_fwd_params*, cudaStream_t) { return fail(-1, "not built"); }
-int umma_conv_dgrad(const b200_conv_dgrad_params*, cudaStream_t) { return fail(-1, "not built"); }
-int umma_conv_wgrad(const b200_conv_wgrad_params*, void*, size_t, cudaStream_t) { return fail(-1, "not built"); }
-size_t umma_conv_wgrad_workspace(const b200_conv_wgrad_params*) { return 0; }
-int umma_convt_fwd(const b200_convt_fwd_params*, cudaStream_t) { return fail(-1, "not built"); }
-int umma_convt_dgrad(const b200_convt_dgrad_params*, cudaStream_t) { return fail(-1, "not built"); }
-int umma_convt_wgrad(const b200_convt_wgrad_params*, void*, size_t, cudaStream_t) { return fail(-1, "not built"); }
-size_t umma_convt_wgrad_workspace(const b200_convt_wgrad_params*) { return 0; }
+
+constexpr int kUmmaThreads = 224;
+constexpr int kNA = 2;        // A (activation tile) stages
+constexpr int kMaxNB = 8;     // B (weight tile) stages
+constexpr uint32_t kSmemBudget = 200 * 1024;
+
+struct TileMaps {
+  CUtensorMap a[4];
+  CUtensorMap b;
+};
+
+struct UmmaArgs {
+  int num_a;
+  int a_c[4];
+  int a_koff[4];
+  int taps, kx, kpad, pad;
+  int P, TH, TW;
+  int tiles_x, tiles_y, n_img, n_ntiles;
+  int Ho, Wo, cout_total;
+  DView dst[4];
+  const bf16* mask[4];
+  int ndst, dst_c0;
+  const float* bias;
+  int relu;
+  uint32_t a_stage_bytes, a_tx_bytes;
+  int nb_stages;
+};
+
+struct TileCoord {
+  int n, y0, x0, n0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const UmmaArgs& a, int tile, int bn) {
+  TileCoord t;
+  const int nt = tile % a.n_ntiles;
+  int pt = tile / a.n_ntiles;
+  const int txi = pt % a.tiles_x;
+  pt /= a.tiles_x;
+  const int tyi = pt % a.tiles_y;
+  t.n = pt / a.tiles_y;
+  t.y0 = tyi * a.TH;
+  t.x0 = txi * a.TW;
+  t.n0 = nt * bn;
+  return t;
+}
+
+template <int MB, int BN>
+__global__ void __launch_bounds__(kUmmaThreads, 1)
+umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ UmmaArgs a) {
+  constexpr int NBUF = (2 * MB * BN <= 512) ? 2 : 1;
+  constexpr uint32_t TMEM_COLS = NBUF * MB * BN;
+  static_assert(TMEM_COLS >= 32 && TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns");
+  constexpr uint32_t B_STAGE_BYTES = BN * 128;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + kNA * a.a_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (uint32_t)a.nb_stages * B_STAGE_BYTES);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + kNA;
+  uint64_t* b_full = a_empty + kNA;
+  uint64_t* b_empty = b_full + kMaxNB;
+  uint64_t* t_full = b_empty + kMaxNB;
+  uint64_t* t_empty = t_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = a.tiles_x * a.tiles_y * a.n_img * a.n_ntiles;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kNA; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < kMaxNB; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&t_full[i], 1);
+      mbar_init(&t_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < a.num_a; ++s) tma_prefetch_desc(&maps.a[s]);
+    tma_prefetch_desc(&maps.b);
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= A producer: one haloed activation tile per (tile, source, 64-channel chunk)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(a, tile, BN);
+        for (int s = 0; s < a.num_a; ++s) {
+          for (int c0 = 0; c0 < a.a_c[s]; c0 += 64) {
+            mbar_wait(&a_empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&a_full[stage], a.a_tx_bytes);
+            tma_load_4d(&maps.a[s], &a_full[stage], sA + stage * a.a_stage_bytes, c0, t.x0 - a.pad, t.y0 - a.pad, t.n);
+            if (++stage == kNA) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= B producer: one [BN x 64] weight tile per (tile, source, chunk, tap)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(a, tile, BN);
+        for (int s = 0; s < a.num_a; ++s) {
+          for (int c0 = 0; c0 < a.a_c[s]; c0 += 64) {
+            for (int tap = 0; tap < a.taps; ++tap) {
+              mbar_wait(&b_empty[stage], phase ^ 1);
+              mbar_arrive_expect_tx(&b_full[stage], B_STAGE_BYTES);
+              tma_load_2d(&maps.b, &b_full[stage], sB + stage * B_STAGE_BYTES, tap * a.kpad + a.a_koff[s] + c0, t.n0);
+              if (++stage == a.nb_stages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ================= MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      constexpr uint64_t desc_hi = umma_desc_hi_sw128(16, 1024);
+      int astage = 0, bstage = 0;
+      uint32_t aphase = 0, bphase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it % NBUF;
+        mbar_wait(&t_empty[buf], ((it / NBUF) & 1) ^ 1);
+        tc_fence_after_sync();
+        const uint32_t acc = tmem_base + buf * (MB * BN);
+        bool first = true;
+        for (int s = 0; s < a.num_a; ++s) {
+          for (int c0 = 0; c0 < a.a_c[s]; c0 += 64) {
+            mbar_wait(&a_full[astage], aphase);
+            const uint32_t a_base = smem_u32(sA + astage * a.a_stage_bytes);
+            for (int tap = 0; tap < a.taps; ++tap) {
+              mbar_wait(&b_full[bstage], bphase);
+              tc_fence_after_sync();
+              const uint32_t b_base = smem_u32(sB + bstage * B_STAGE_BYTES);
+              const int r = tap / a.kx, sx = tap - r * a.kx;
+              const uint32_t a_tap = a_base + (uint32_t)(r * a.P + sx) * 128;
+#pragma unroll
+              for (int mb = 0; mb < MB; ++mb) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                  // the first MMA into each M-block's accumulator overwrites, everything after accumulates
+                  umma_bf16(acc + mb * BN, umma_desc(desc_hi, a_tap + mb * (128 * 128) + kk * 32),
+                            umma_desc(desc_hi, b_base + kk * 32), idesc, (first && kk == 0) ? 0u : 1u);
+                }
+              }
+              first = false;
+              umma_commit(&b_empty[bstage]);
+              if (++bstage == a.nb_stages) {
+                bstage = 0;
+                bphase ^= 1;
+              }
+            }
+            umma_commit(&a_empty[astage]);
+            if (++astage == kNA) {
+              astage = 0;
+              aphase ^= 1;
+            }
+          }
+        }
+        umma_commit(&t_full[buf]);
+      }
+    }
+  } else {
+    // ================= epilogue: 4 warps, warp w owns TMEM lanes 32*(w%4) .. +31
+    const int quarter = warp & 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const TileCoord t = decode_tile(a, tile, BN);
+      const int buf = it % NBUF;
+      mbar_wait(&t_full[buf], (it / NBUF) & 1);
+      tc_fence_after_sync();
+      const int d = a.ndst > 1 ? min(t.n0 / a.dst_c0, a.ndst - 1) : 0;
+      const int ch0 = t.n0 - d * a.dst_c0;
+      const DView& dst = a.dst[d];
+      const bf16* mk = a.mask[d];
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb) {
+        const int q = mb * 128 + quarter * 32 + lane;
+        const int ty = q / a.P, tx = q - ty * a.P;
+        const int oy = t.y0 + ty, ox = t.x0 + tx;
+        const bool valid = ty < a.TH && tx < a.TW && oy < a.Ho && ox < a.Wo;
+        const long long off = valid ? dst.off(t.n, oy, ox) + ch0 : 0;
+        const uint32_t taddr = tmem_base + buf * (MB * BN) + mb * BN + (uint32_t(quarter * 32) << 16);
+#pragma unroll 1
+        for (int col0 = 0; col0 < BN; col0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + col0, v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {
+              const int col = col0 + g8 * 8;
+              if (t.n0 + col < a.cout_total) {
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g8 * 8 + j]);
+                if (a.bias) {
+                  const float4 b0 = *reinterpret_cast<const float4*>(a.bias + ch0 + col);
+                  const float4 b1 = *reinterpret_cast<const float4*>(a.bias + ch0 + col + 4);
+                  f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                  f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                }
+                if (a.relu) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+                }
+                if (mk) {
+                  float m[8];
+                  unpack8(*reinterpret_cast<const bf16x8*>(mk + off + col), m);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) f[j] = m[j] > 0.f ? f[j] : 0.f;
+                }
+                *reinterpret_cast<bf16x8*>(dst.p + off + col) = pack8(f);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[buf]);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------ host side
+struct Plan {
+  int MB, BN, P, TH, TW, halo;
+  int tiles_x, tiles_y, n_ntiles;
+  uint32_t a_stage_bytes, a_tx_bytes, smem_bytes;
+  int nb_stages;
+};
+
+static bool aligned_view(const b200_view& v) {
+  return v.c % 8 == 0 && reinterpret_cast<uintptr_t>(v.ptr) % 16 == 0 && v.stride_w % 8 == 0 && v.stride_h % 8 == 0 &&
+         (v.n == 1 || v.stride_n % 8 == 0);
+}
+
+static bool device_is_sm100() {
+  static int cached = -1;
+  if (cached < 0) cached = b200unet_device_ok();
+  return cached == 1;
+}
+
+static int pick_bn(int cout_total, int ndst, int dst_c0) {
+  const int cands[4] = {256, 128, 64, 32};
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands[i];
+    if (cout_total % bn == 0 && (ndst == 1 || dst_c0 % bn == 0)) return bn;
+  }
+  return ndst == 1 ? 32 : 0;  // partial last N-tile handled by the column predicate
+}
+
+// Chooses tile geometry (MB M-blocks of 128 positions, pitch P, TH rows) minimising issued MMA rows.
+static bool make_plan(int Ho, int Wo, int n_img, int halo, int cout_total, int ndst, int dst_c0, Plan* pl) {
+  int bn = pick_bn(cout_total, ndst, dst_c0);
+  if (bn == 0) return false;
+  pl->halo = halo;
+  double best = 1e30;
+  bool found = false;
+  for (int mb = 1; mb <= 2; ++mb) {
+    if (mb * bn > 512) continue;
+    for (int P = halo + 1; P <= 256 && P <= Wo + halo + 8; ++P) {
+      const int TW = P - halo;
+      int TH = (mb * 128) / P;
+      if (TH < 1) break;
+      if (TH > Ho) TH = Ho;
+      if (TH + halo > 256) continue;
+      const uint32_t rows = (uint32_t)max((TH + halo) * P, mb * 128 + halo * P + halo);
+      const uint32_t a_stage = (rows * 128 + 1023) & ~1023u;
+      if (kNA * a_stage + 2 * (uint32_t)bn * 128 + 1024 > kSmemBudget) continue;
+      const long long tiles = (long long)((Wo + TW - 1) / TW) * ((Ho + TH - 1) / TH) * n_img;
+      // cost: MMA rows issued, + fixed per-tile overhead, + mild preference for MB = 2 (halves weight traffic)
+      double cost = (double)tiles * (mb * 128 + 24) * (mb == 1 ? 1.06 : 1.0);
+      if (cost < best) {
+        best = cost;
+        found = true;
+        pl->MB = mb;
+        pl->P = P;
+        pl->TH = TH;
+        pl->TW = TW;
+        pl->a_stage_bytes = a_stage;
+      }
+    }
+  }
+  if (!found) return false;
+  pl->BN = bn;
+  pl->tiles_x = (Wo + pl->TW - 1) / pl->TW;
+  pl->tiles_y = (Ho + pl->TH - 1) / pl->TH;
+  pl->n_ntiles = (cout_total + bn - 1) / bn;
+  pl->a_tx_bytes = (uint32_t)(pl->TH + halo) * pl->P * 128;
+  int nb = (int)((kSmemBudget - 1024 - kNA * pl->a_stage_bytes) / ((uint32_t)bn * 128));
+  if (nb > kMaxNB) nb = kMaxNB;
+  if (nb < 2) return false;
+  pl->nb_stages = nb;
+  pl->smem_bytes = kNA * pl->a_stage_bytes + nb * bn * 128 + 1024 /*align*/ + 512 /*barriers*/;
+  return true;
+}
+
+static int make_a_map(CUtensorMap* m, const b200_view& v, int P, int rows) {
+  uint64_t dims[4] = {(uint64_t)v.c, (uint64_t)v.w, (uint64_t)v.h, (uint64_t)v.n};
+  uint64_t strides[3] = {(uint64_t)v.stride_w * 2, (uint64_t)v.stride_h * 2,
+                         (uint64_t)(v.n > 1 ? v.stride_n : (int64_t)v.stride_h * v.h) * 2};
+  uint32_t box[4] = {64, (uint32_t)P, (uint32_t)rows, 1};
+  return make_tmap_bf16(m, v.ptr, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+static int make_b_map(CUtensorMap* m, const void* w, int rows, int cols, int bn) {
+  uint64_t dims[2] = {(uint64_t)cols, (uint64_t)rows};
+  uint64_t strides[1] = {(uint64_t)cols * 2};
+  uint32_t box[2] = {64, (uint32_t)bn};
+  return make_tmap_bf16(m, w, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+template <int MB, int BN>
+static int launch_inst(const TileMaps& maps, const UmmaArgs& a, const Plan& pl, cudaStream_t st) {
+  auto kern = umma_conv_kernel<MB, BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget + 2048);
+    if (e != cudaSuccess) return fail((int)e, "umma_conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_done = true;
+  }
+  const int total = a.tiles_x * a.tiles_y * a.n_img * a.n_ntiles;
+  static int sms = 0;
+  if (!sms) sms = b200unet_num_sms();
+  const int grid = total < sms ? total : sms;
+  kern<<<grid, kUmmaThreads, pl.smem_bytes, st>>>(maps, a);
+  return check_launch("umma_conv");
+}
+
+static int launch_plan(const TileMaps& maps, UmmaArgs& a, const Plan& pl, cudaStream_t st) {
+  a.P = pl.P;
+  a.TH = pl.TH;
+  a.TW = pl.TW;
+  a.tiles_x = pl.tiles_x;
+  a.tiles_y = pl.tiles_y;
+  a.n_ntiles = pl.n_ntiles;
+  a.a_stage_bytes = pl.a_stage_bytes;
+  a.a_tx_bytes = pl.a_tx_bytes;
+  a.nb_stages = pl.nb_stages;
+#define B200_INST(MBv, BNv) \
+  if (pl.MB == MBv && pl.BN == BNv) return launch_inst<MBv, BNv>(maps, a, pl, st);
+  B200_INST(1, 32)
+  B200_INST(1, 64)
+  B200_INST(1, 128)
+  B200_INST(1, 256)
+  B200_INST(2, 32)
+  B200_INST(2, 64)
+  B200_INST(2, 128)
+  B200_INST(2, 256)
+#undef B200_INST
+  return fail(-1, "umma_conv: no kernel instance for MB=%d BN=%d", pl.MB, pl.BN);
+}
+
+// ------------------------------------------------------------------ conv forward
+bool umma_conv_fwd_ok(const b200_conv_fwd_params* p) {
+  if (!device_is_sm100()) return false;
+  for (int i = 0; i < p->num_src; ++i)
+    if (!aligned_view(p->src[i])) return false;
+  if (!aligned_view(p->dst)) return false;
+  if (p->bias && reinterpret_cast<uintptr_t>(p->bias) % 16 != 0) return false;
+  Plan pl;
+  return make_plan(p->dst.h, p->dst.w, p->dst.n, p->taps == 9 ? 2 : 0, p->dst.c, 1, p->dst.c, &pl);
+}
+
+int umma_conv_fwd(const b200_conv_fwd_params* p, cudaStream_t st) {
+  if (!p->w_packed) return fail(-1, "conv_fwd (tcgen05): w_packed is required");
+  const int halo = p->taps == 9 ? 2 : 0;
+  Plan pl;
+  if (!make_plan(p->dst.h, p->dst.w, p->dst.n, halo, p->dst.c, 1, p->dst.c, &pl)) return fail(-1, "conv_fwd: no plan");
+  TileMaps maps;
+  UmmaArgs a{};
+  a.num_a = p->num_src;
+  int koff = 0;
+  for (int i = 0; i < p->num_src; ++i) {
+    int r = make_a_map(&maps.a[i], p->src[i], pl.P, pl.TH + halo);
+    if (r) return fail(r, "conv_fwd: tensor map for src[%d] failed (%d)", i, r);
+    a.a_c[i] = p->src[i].c;
+    a.a_koff[i] = koff;
+    koff += (p->src[i].c + 63) / 64 * 64;
+  }
+  a.kpad = koff;
+  int r = make_b_map(&maps.b, p->w_packed, p->dst.c, p->taps * a.kpad, pl.BN);
+  if (r) return fail(r, "conv_fwd: weight tensor map failed (%d)", r);
+  a.taps = p->taps;
+  a.kx = p->taps == 9 ? 3 : 1;
+  a.pad = p->pad;
+  a.n_img = p->dst.n;
+  a.Ho = p->dst.h;
+  a.Wo = p->dst.w;
+  a.cout_total = p->dst.c;
+  a.dst[0] = dview(p->dst);
+  a.ndst = 1;
+  a.dst_c0 = p->dst.c;
+  a.bias = p->bias;
+  a.relu = p->relu;
+  return launch_plan(maps, a, pl, st);
+}
+
+// ------------------------------------------------------------------ conv backward-data
+static int dgrad_cin(const b200_conv_dgrad_params* p) {
+  int c = 0;
+  for (int i = 0; i < p->num_dst; ++i) c += p->dst[i].c;
+  return c;
+}
+
+bool umma_conv_dgrad_ok(const b200_conv_dgrad_params* p) {
+  if (!device_is_sm100()) return false;
+  if (!aligned_view(p->dz)) return false;
+  for (int i = 0; i < p->num_dst; ++i) {
+    if (!aligned_view(p->dst[i])) return false;
+    if (reinterpret_cast<uintptr_t>(p->mask[i]) % 16 != 0) return false;
+  }
+  Plan pl;
+  return make_plan(p->dst[0].h, p->dst[0].w, p->dst[0].n, p->taps == 9 ? 2 : 0, dgrad_cin(p), p->num_dst, p->dst[0].c,
+                   &pl);
+}
+
+int umma_conv_dgrad(const b200_conv_dgrad_params* p, cudaStream_t st) {
+  if (!p->w_packed) return fail(-1, "conv_dgrad (tcgen05): w_packed is required");
+  const int halo = p->taps == 9 ? 2 : 0;
+  const int cin = dgrad_cin(p);
+  Plan pl;
+  if (!make_plan(p->dst[0].h, p->dst[0].w, p->dst[0].n, halo, cin, p->num_dst, p->dst[0].c, &pl))
+    return fail(-1, "conv_dgrad: no plan");
+  TileMaps maps;
+  UmmaArgs a{};
+  a.num_a = 1;
+  int r = make_a_map(&maps.a[0], p->dz, pl.P, pl.TH + halo);
+  if (r) return fail(r, "conv_dgrad: tensor map for dz failed (%d)", r);
+  a.a_c[0] = p->dz.c;
+  a.a_koff[0] = 0;
+  a.kpad = (p->dz.c + 63) / 64 * 64;
+  r = make_b_map(&maps.b, p->w_packed, cin, p->taps * a.kpad, pl.BN);
+  if (r) return fail(r, "conv_dgrad: weight tensor map failed (%d)", r);
+  a.taps = p->taps;
+  a.kx = p->taps == 9 ? 3 : 1;
+  a.pad = halo - p->pad;  // full correlation with the flipped filter
+  a.n_img = p->dst[0].n;
+  a.Ho = p->dst[0].h;
+  a.Wo = p->dst[0].w;
+  a.cout_total = cin;
+  a.ndst = p->num_dst;
+  a.dst_c0 = p->dst[0].c;
+  for (int i = 0; i < p->num_dst; ++i) {
+    a.dst[i] = dview(p->dst[i]);
+    a.mask[i] = (const bf16*)p->mask[i];
+  }
+  return launch_plan(maps, a, pl, st);
+}
+
+// ------------------------------------------------------------------ ConvTranspose2d forward / backward-data
+static b200_view quadrant(const b200_view& big, int ab) {
+  b200_view q = big;
+  q.ptr = (char*)big.ptr + ((int64_t)(ab >> 1) * big.stride_h + (int64_t)(ab & 1) * big.stride_w) * 2;
+  q.h = big.h / 2;
+  q.w = big.w / 2;
+  q.stride_h = big.stride_h * 2;
+  q.stride_w = big.stride_w * 2;
+  return q;
+}
+
+bool umma_convt_fwd_ok(const b200_convt_fwd_params* p) {
+  if (!device_is_sm100()) return false;
+  if (!aligned_view(p->x) || !aligned_view(p->y)) return false;
+  if (p->bias && reinterpret_cast<uintptr_t>(p->bias) % 16 != 0) return false;
+  Plan pl;
+  return make_plan(p->x.h, p->x.w, p->x.n, 0, 4 * p->y.c, 4, p->y.c, &pl);
+}
+
+int umma_convt_fwd(const b200_convt_fwd_params* p, cudaStream_t st) {
+  if (!p->w_packed) return fail(-1, "convt_fwd (tcgen05): w_packed is required");
+  Plan pl;
+  if (!make_plan(p->x.h, p->x.w, p->x.n, 0, 4 * p->y.c, 4, p->y.c, &pl)) return fail(-1, "convt_fwd: no plan");
+  TileMaps maps;
+  UmmaArgs a{};
+  a.num_a = 1;
+  int r = make_a_map(&maps.a[0], p->x, pl.P, pl.TH);
+  if (r) return fail(r, "convt_fwd: tensor map for x failed (%d)", r);
+  a.a_c[0] = p->x.c;
+  a.kpad = (p->x.c + 63) / 64 * 64;
+  r = make_b_map(&maps.b, p->w_packed, 4 * p->y.c, a.kpad, pl.BN);
+  if (r) return fail(r, "convt_fwd: weight tensor map failed (%d)", r);
+  a.taps = 1;
+  a.kx = 1;
+  a.pad = 0;
+  a.n_img = p->x.n;
+  a.Ho = p->x.h;
+  a.Wo = p->x.w;
+  a.cout_total = 4 * p->y.c;
+  a.ndst = 4;
+  a.dst_c0 = p->y.c;
+  for (int ab = 0; ab < 4; ++ab) a.dst[ab] = dview(quadrant(p->y, ab));
+  a.bias = p->bias;
+  return launch_plan(maps, a, pl, st);
+}
+
+bool umma_convt_dgrad_ok(const b200_convt_dgrad_params* p) {
+  if (!device_is_sm100()) return false;
+  if (!aligned_view(p->dx) || !aligned_view(p->dy)) return false;
+  if (reinterpret_cast<uintptr_t>(p->mask) % 16 != 0) return false;
+  Plan pl;
+  return make_plan(p->dx.h, p->dx.w, p->dx.n, 0, p->dx.c, 1, p->dx.c, &pl);
+}
+
+int umma_convt_dgrad(const b200_convt_dgrad_params* p, cudaStream_t st) {
+  if (!p->w_packed) return fail(-1, "convt_dgrad (tcgen05): w_packed is required");
+  Plan pl;
+  if (!make_plan(p->dx.h, p->dx.w, p->dx.n, 0, p->dx.c, 1, p->dx.c, &pl)) return fail(-1, "convt_dgrad: no plan");
+  TileMaps maps;
+  UmmaArgs a{};
+  a.num_a = 4;
+  const int opad = (p->dy.c + 63) / 64 * 64;
+  for (int ab = 0; ab < 4; ++ab) {
+    int r = make_a_map(&maps.a[ab], quadrant(p->dy, ab), pl.P, pl.TH);
+    if (r) return fail(r, "convt_dgrad: tensor map for dy quadrant %d failed (%d)", ab, r);
+    a.a_c[ab] = p->dy.c;
+    a.a_koff[ab] = ab * opad;
+  }
+  a.kpad = 4 * opad;
+  int r = make_b_map(&maps.b, p->w_packed, p->dx.c, 4 * opad, pl.BN);
+  if (r) return fail(r, "convt_dgrad: weight tensor map failed (%d)", r);
+  a.taps = 1;
+  a.kx = 1;
+  a.pad = 0;
+  a.n_img = p->dx.n;
+  a.Ho = p->dx.h;
+  a.Wo = p->dx.w;
+  a.cout_total = p->dx.c;
+  a.ndst = 1;
+  a.dst_c0 = p->dx.c;
+  a.dst[0] = dview(p->dx);
+  a.mask[0] = (const bf16*)p->mask;
+  return launch_plan(maps, a, pl, st);
+}
+
+// backward-weights on tensor cores: wgrad_umma.cu
 }  // namespace b200
