@@ -132,6 +132,8 @@ const char* b200unet_last_error(void);
 /* 1 if the tcgen05 path can run on the current device (sm_100) */
 int b200unet_device_ok(void);
 int b200unet_num_sms(void);
+/* number of kernel launches this library has made in this process (for bench.py's gpu_launches) */
+unsigned long long b200unet_launch_count(void);
 
 int b200unet_conv_fwd(const b200_conv_fwd_params* p, void* stream);
 int b200unet_conv_dgrad(const b200_conv_dgrad_params* p, void* stream);

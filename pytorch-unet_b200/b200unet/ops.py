@@ -287,13 +287,15 @@ def head_fwd(x, w, b, relu: bool) -> torch.Tensor:
     return logits
 
 
-def head_bwd(x, w, b, relu: bool, dlogits, dx=None, mask=None, want_dx: bool = True):
+def head_bwd(x, w, b, relu: bool, dlogits, dx=None, mask=None, want_dx: bool = True, dw=None, db=None):
     lib = _lib.load()
     k, c = w.shape[0], x.shape[3]
     if dx is None and want_dx:
         dx = torch.empty_like(x)
-    dw = torch.empty((k, c, 1, 1), dtype=torch.float32, device=x.device)
-    db = torch.empty((k,), dtype=torch.float32, device=x.device)
+    if dw is None:
+        dw = torch.empty((k, c, 1, 1), dtype=torch.float32, device=x.device)
+    if db is None:
+        db = torch.empty((k,), dtype=torch.float32, device=x.device)
     ws = workspace(lib.b200unet_head_workspace_bytes(c, k), x.device)
     vx = view(x)
     vdx = view(dx) if dx is not None else None
@@ -320,13 +322,16 @@ def head_ce_fwd(x, w, b, relu: bool, labels, want_logits: bool = False):
     return loss, state, logits
 
 
-def head_ce_bwd(x, w, b, relu: bool, labels, state, grad_scale=None, dx=None, mask=None, want_dx: bool = True):
+def head_ce_bwd(x, w, b, relu: bool, labels, state, grad_scale=None, dx=None, mask=None, want_dx: bool = True,
+                dw=None, db=None):
     lib = _lib.load()
     k, c = w.shape[0], x.shape[3]
     if dx is None and want_dx:
         dx = torch.empty_like(x)
-    dw = torch.empty((k, c, 1, 1), dtype=torch.float32, device=x.device)
-    db = torch.empty((k,), dtype=torch.float32, device=x.device)
+    if dw is None:
+        dw = torch.empty((k, c, 1, 1), dtype=torch.float32, device=x.device)
+    if db is None:
+        db = torch.empty((k,), dtype=torch.float32, device=x.device)
     ws = workspace(lib.b200unet_head_workspace_bytes(c, k), x.device)
     vx = view(x)
     vdx = view(dx) if dx is not None else None

@@ -164,6 +164,7 @@ class UNet(nn.Module):
         # hooks for the data-parallel wrapper: grad arena allocator + "these gradients are final" callback
         self._grad_alloc: Optional[Callable[[str, Tuple[int, ...], torch.device], torch.Tensor]] = None
         self._grad_ready: Optional[Callable[[str], None]] = None
+        self._grads_done: Optional[Callable[[], None]] = None
         self._pack_cache: Dict[Tuple[str, int], Tuple[int, int, torch.Tensor]] = {}
 
     # ---------------------------------------------------------------- public API
@@ -323,16 +324,14 @@ class UNet(nn.Module):
         hx, hact = tape.head["x"], tape.head["act"]
         g = torch.empty_like(hx)
         mask = None if bn else hact
-        if labels is None:
-            _, dw, db = ops.head_bwd(hx, hw2, hb.detach(), self.non_neg, grad_out.float(), dx=g, mask=mask)
-        else:
-            gs = grad_out.detach().reshape(1).float()
-            _, dw, db = ops.head_ce_bwd(hx, hw2, hb.detach(), self.non_neg, labels.contiguous(), tape.head["state"],
-                                        grad_scale=gs, dx=g, mask=mask)
         dwh = self._new_grad(hname + ".weight", hw)
         dbh = self._new_grad(hname + ".bias", hb)
-        dwh.copy_(dw.view_as(dwh))
-        dbh.copy_(db)
+        if labels is None:
+            ops.head_bwd(hx, hw2, hb.detach(), self.non_neg, grad_out.float(), dx=g, mask=mask, dw=dwh, db=dbh)
+        else:
+            gs = grad_out.detach().reshape(1).float()
+            ops.head_ce_bwd(hx, hw2, hb.detach(), self.non_neg, labels.contiguous(), tape.head["state"],
+                            grad_scale=gs, dx=g, mask=mask, dw=dwh, db=dbh)
         grads[hname + ".weight"], grads[hname + ".bias"] = dwh, dbh
         self._done(hname + ".weight", hname + ".bias")
 
@@ -386,4 +385,6 @@ class UNet(nn.Module):
                 gp = torch.empty(prev_pooled_shape, dtype=torch.bfloat16, device=g.device)
                 self._block_backward(f"down_path.{i}", down, tape, P, g, grads, [gp], [None])
                 g = gp
+        if self._grads_done is not None:
+            self._grads_done()
         return grads

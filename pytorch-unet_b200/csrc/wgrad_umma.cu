@@ -1,10 +1,458 @@
-// tcgen05 backward-weights (placeholder until the kernel lands): reports every shape as unsupported.
+// tcgen05 backward-weights kernel for the convolution family:
+//   conv 3x3 / 1x1:   dW[o][c][r][s] = sum_{n,y,x} dz[n,y,x,o] * x[n,y+r-pad,x+s-pad,c]      (two concatenated sources)
+//   ConvTranspose2d:  dW[c][o][a][b] = sum_{n,i,j} x[n,i,j,c] * dy[n,2i+a,2j+b,o]
+//
+// GEMM view (per filter tap): D_tap[M = row-operand channels, N = gathered-operand channels] += R^T * G_tap, with the
+// PIXELS as the contraction dimension.  NHWC makes both operands "MN-major" (channels contiguous, one 128-byte
+// SWIZZLE_128B row per pixel), which tcgen05 consumes directly: no transpose pass anywhere.
+//   R tile ("row operand": dz, or x for the transposed conv): TH x TW pixels stored with pitch P = TW + halo; the halo
+//     columns and the rows past TH*P stay zero (zero-filled once, TMA never touches them), so they add nothing.
+//   G tile ("gathered operand": x, or the four stride-2 sub-lattices of dy): (TH+halo) x P pixels, loaded once; tap
+//     (r, s) is the same buffer read through a descriptor advanced by r*P + s rows — the same shifted-descriptor
+//     trick as the forward kernel, now on the K axis.
+// Accumulators: one [128 x 64] fp32 block per tap in TMEM; 9 taps x 64 columns do not fit in 512, so a 3x3 runs as two
+// tap groups (5 + 4) that are separate work items.  Work item = (pixel split, tap group, 64-channel N block, 128-channel
+// M block); partial sums go to a fp32 workspace [split][tap][M][N] and a second kernel reduces the splits in a fixed
+// order and writes the state_dict layout, so results are run-to-run reproducible.
+#include "chan_reduce.cuh"
 #include "conv_impl.h"
+#include "ptx.cuh"
+#include "tmap.h"
+
 namespace b200 {
-bool umma_conv_wgrad_ok(const b200_conv_wgrad_params*) { return false; }
-bool umma_convt_wgrad_ok(const b200_convt_wgrad_params*) { return false; }
-int umma_conv_wgrad(const b200_conv_wgrad_params*, void*, size_t, cudaStream_t) { return fail(-1, "not built"); }
-size_t umma_conv_wgrad_workspace(const b200_conv_wgrad_params*) { return 0; }
-int umma_convt_wgrad(const b200_convt_wgrad_params*, void*, size_t, cudaStream_t) { return fail(-1, "not built"); }
-size_t umma_convt_wgrad_workspace(const b200_convt_wgrad_params*) { return 0; }
+
+constexpr int kWgThreads = 192;  // warp 0 producer, warp 1 MMA, warps 2..5 epilogue
+constexpr int kWgMaxStages = 4;
+constexpr uint32_t kWgSmemBudget = 200 * 1024;
+
+struct WgMaps {
+  CUtensorMap r;     // row operand
+  CUtensorMap g[4];  // gathered operand(s): conv = one per concat source, convT = one per (a, b) sub-lattice
+};
+
+struct WgArgs {
+  int mode;  // 0 = conv (taps share one G tile), 1 = convT (one G tile per tap)
+  int m_total, n_total;
+  int g_c[2];       // conv: channels per concat source
+  int n_blks0;      // conv: number of 64-blocks of source 0
+  int taps, kx, halo, pad;
+  int P, TH, TW, kt_rows;
+  int tiles_x, tiles_y, n_img;
+  int m_blks, n_blks, tap_groups, splits;
+  int m_pad, n_pad;
+  float* ws;
+  uint32_t r_blk_bytes, g_tile_bytes, g_box_bytes, stage_bytes;
+  int stages;
+  int r_blocks;  // 64-channel blocks of the row operand actually loaded (1 or 2)
+};
+
+struct WgItem {
+  int split, grp, nb, mb;
+  int tap0, ntap;
+  int tile0, tile1;
+};
+
+__device__ __forceinline__ WgItem decode_item(const WgArgs& a, int item) {
+  WgItem w;
+  w.mb = item % a.m_blks;
+  item /= a.m_blks;
+  w.nb = item % a.n_blks;
+  item /= a.n_blks;
+  w.grp = item % a.tap_groups;
+  w.split = item / a.tap_groups;
+  const int per = (a.taps + a.tap_groups - 1) / a.tap_groups;
+  w.tap0 = w.grp * per;
+  w.ntap = min(per, a.taps - w.tap0);
+  const long long total = (long long)a.tiles_x * a.tiles_y * a.n_img;
+  w.tile0 = (int)(total * w.split / a.splits);
+  w.tile1 = (int)(total * (w.split + 1) / a.splits);
+  return w;
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (uint32_t)a.stages * a.stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = full + kWgMaxStages;
+  uint64_t* t_full = empty + kWgMaxStages;
+  uint64_t* t_empty = t_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_items = a.m_blks * a.n_blks * a.tap_groups * a.splits;
+  const int g_tiles = a.mode == 1 ? a.taps : 1;
+
+  // zero the whole pipeline once: halo columns / tail rows of the R tiles and the unused tail of the G tiles must
+  // read as 0 (never NaN bit patterns); TMA only ever writes the box interiors afterwards.
+  {
+    uint4* p = reinterpret_cast<uint4*>(smem);
+    const uint32_t n16 = (uint32_t)a.stages * a.stage_bytes / 16;
+    for (uint32_t i = threadIdx.x; i < n16; i += kWgThreads) p[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWgMaxStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(t_full, 1);
+    mbar_init(t_empty, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&maps.r);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const WgItem w = decode_item(a, item);
+        // gathered-operand source of this N block
+        int gsrc = 0, gc0 = w.nb * 64;
+        if (a.mode == 0 && w.nb >= a.n_blks0) {
+          gsrc = 1;
+          gc0 = (w.nb - a.n_blks0) * 64;
+        }
+        for (int tile = w.tile0; tile < w.tile1; ++tile) {
+          const int txi = tile % a.tiles_x;
+          const int tyi = (tile / a.tiles_x) % a.tiles_y;
+          const int n = tile / (a.tiles_x * a.tiles_y);
+          const int y0 = tyi * a.TH, x0 = txi * a.TW;
+          uint8_t* st = smem + stage * a.stage_bytes;
+          mbar_wait(&empty[stage], phase ^ 1);
+          const uint32_t tx_bytes = (uint32_t)a.r_blocks * a.TH * a.TW * 128 + (uint32_t)g_tiles * a.g_box_bytes;
+          mbar_arrive_expect_tx(&full[stage], tx_bytes);
+          // R tile: one TMA per tile row so that rows land with pitch P (halo columns stay zero)
+          for (int rb = 0; rb < a.r_blocks; ++rb)
+            for (int ty = 0; ty < a.TH; ++ty)
+              tma_load_4d(&maps.r, &full[stage], st + rb * a.r_blk_bytes + (uint32_t)(ty * a.P) * 128,
+                          w.mb * 128 + rb * 64, x0, y0 + ty, n);
+          uint8_t* gt = st + 2 * a.r_blk_bytes;
+          if (a.mode == 0) {
+            tma_load_4d(&maps.g[gsrc], &full[stage], gt, gc0, x0 - a.pad, y0 - a.pad, n);
+          } else {
+            for (int t = 0; t < a.taps; ++t)
+              tma_load_4d(&maps.g[t], &full[stage], gt + t * a.g_tile_bytes, gc0, x0, y0, n);
+          }
+          if (++stage == a.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);  // both operands MN-major
+      const uint64_t hi_r = umma_desc_hi_sw128(a.r_blk_bytes, 1024);
+      const uint64_t hi_g = umma_desc_hi_sw128(a.r_blk_bytes, 1024);  // N = 64: a single block, LBO unused
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      const int ksteps = a.kt_rows / 16;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+        const WgItem w = decode_item(a, item);
+        mbar_wait(t_empty, (it & 1) ^ 1);
+        tc_fence_after_sync();
+        bool first = true;
+        for (int tile = w.tile0; tile < w.tile1; ++tile) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t r_base = smem_u32(smem + stage * a.stage_bytes);
+          const uint32_t g_base = r_base + 2 * a.r_blk_bytes;
+          for (int j = 0; j < w.ntap; ++j) {
+            const int tap = w.tap0 + j;
+            uint32_t g_tap;
+            if (a.mode == 0) {
+              const int r = tap / a.kx, sx = tap - r * a.kx;
+              g_tap = g_base + (uint32_t)(r * a.P + sx) * 128;
+            } else {
+              g_tap = g_base + tap * a.g_tile_bytes;
+            }
+            for (int k = 0; k < ksteps; ++k)
+              umma_bf16(tmem_base + j * 64, umma_desc(hi_r, r_base + k * 2048), umma_desc(hi_g, g_tap + k * 2048), idesc,
+                        (first && k == 0) ? 0u : 1u);
+          }
+          first = false;
+          umma_commit(&empty[stage]);
+          if (++stage == a.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(t_full);
+      }
+    }
+  } else {
+    // epilogue: TMEM -> fp32 partials ws[split][tap][m][n]
+    const int quarter = warp & 3;
+    int it = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+      const WgItem w = decode_item(a, item);
+      mbar_wait(t_full, it & 1);
+      tc_fence_after_sync();
+      const int m = w.mb * 128 + quarter * 32 + lane;
+      const bool empty_item = w.tile1 <= w.tile0;  // no MMA was issued: the accumulator holds stale data
+      for (int j = 0; j < w.ntap; ++j) {
+        const int tap = w.tap0 + j;
+        float* out = a.ws + (((long long)w.split * a.taps + tap) * a.m_pad + m) * a.n_pad + w.nb * 64;
+#pragma unroll 1
+        for (int col0 = 0; col0 < 64; col0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + j * 64 + col0 + (uint32_t(quarter * 32) << 16), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            float4 f;
+            f.x = empty_item ? 0.f : __uint_as_float(v[q4 * 4 + 0]);
+            f.y = empty_item ? 0.f : __uint_as_float(v[q4 * 4 + 1]);
+            f.z = empty_item ? 0.f : __uint_as_float(v[q4 * 4 + 2]);
+            f.w = empty_item ? 0.f : __uint_as_float(v[q4 * 4 + 3]);
+            *reinterpret_cast<float4*>(out + col0 + q4 * 4) = f;
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// dw[(m * n_total + n) * taps + tap] = sum_s ws[s][tap][m][npad(n)]
+__global__ void wgrad_umma_reduce_kernel(const float* __restrict__ ws, int splits, int taps, int m_total, int n_total,
+                                         int m_pad, int n_pad, int c_src0, int n_blks0, float* __restrict__ dw) {
+  const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e >= (long long)m_total * n_total) return;
+  const int n = (int)(e % n_total), m = (int)(e / n_total);
+  const int np = n < c_src0 ? n : n_blks0 * 64 + (n - c_src0);
+  for (int t = 0; t < taps; ++t) {
+    float s = 0.f;
+    for (int i = 0; i < splits; ++i) s += ws[(((long long)i * taps + t) * m_pad + m) * n_pad + np];
+    dw[e * taps + t] = s;
+  }
+}
+
+// ------------------------------------------------------------------ host side
+struct WgPlan {
+  WgArgs a;
+  size_t ws_bytes;
+  uint32_t smem_bytes;
+  int grid;
+};
+
+static bool wg_aligned(const b200_view& v) {
+  return v.c % 8 == 0 && reinterpret_cast<uintptr_t>(v.ptr) % 16 == 0 && v.stride_w % 8 == 0 && v.stride_h % 8 == 0 &&
+         (v.n == 1 || v.stride_n % 8 == 0);
+}
+
+static bool wg_device_ok() {
+  static int cached = -1;
+  if (cached < 0) cached = b200unet_device_ok();
+  return cached == 1;
+}
+
+static int wg_sms() {
+  static int sms = 0;
+  if (!sms) sms = b200unet_num_sms();
+  return sms > 0 ? sms : kNumSMsB200;
+}
+
+// row operand extent Ho x Wo x n_img; M = row channels, N = gathered channels (per source for conv)
+static bool wg_make_plan(int mode, int Ho, int Wo, int n_img, int m_total, int n_total, int c_src0, int taps, int pad,
+                         WgPlan* pl) {
+  WgArgs& a = pl->a;
+  a = WgArgs{};
+  a.mode = mode;
+  a.m_total = m_total;
+  a.n_total = n_total;
+  a.taps = taps;
+  a.kx = taps == 9 ? 3 : (taps == 4 ? 2 : 1);
+  a.halo = (mode == 0 && taps == 9) ? 2 : 0;
+  a.pad = pad;
+  a.n_img = n_img;
+  a.g_c[0] = c_src0;
+  a.g_c[1] = n_total - c_src0;
+  a.n_blks0 = (c_src0 + 63) / 64;
+  a.n_blks = a.n_blks0 + (mode == 0 ? (a.g_c[1] + 63) / 64 : 0);
+  a.m_blks = (m_total + 127) / 128;
+  a.r_blocks = m_total > 64 ? 2 : 1;
+  a.tap_groups = taps == 9 ? 2 : 1;
+  a.m_pad = a.m_blks * 128;
+  a.n_pad = a.n_blks * 64;
+  const int g_tiles = mode == 1 ? taps : 1;
+  // tile geometry: kt_rows (multiple of 16) K rows per tile; minimise issued K rows
+  double best = 1e30;
+  bool found = false;
+  for (int kt = 64; kt <= 256; kt += 16) {
+    for (int P = a.halo + 1; P <= 256 && P <= Wo + a.halo + 8; ++P) {
+      const int TW = P - a.halo;
+      int TH = kt / P;
+      if (TH < 1) break;
+      if (TH > Ho) TH = Ho;
+      const uint32_t r_blk = (uint32_t)kt * 128;
+      const uint32_t g_rows = (uint32_t)max((TH + a.halo) * P, kt + a.halo * P + a.halo);
+      const uint32_t g_tile = (g_rows * 128 + 1023) & ~1023u;
+      const uint32_t stage = 2 * r_blk + g_tiles * g_tile;
+      if (2 * stage + 1024 > kWgSmemBudget) continue;
+      const long long tiles = (long long)((Wo + TW - 1) / TW) * ((Ho + TH - 1) / TH) * n_img;
+      const double cost = (double)tiles * (kt + 24);
+      if (cost < best) {
+        best = cost;
+        found = true;
+        a.kt_rows = kt;
+        a.P = P;
+        a.TH = TH;
+        a.TW = TW;
+        a.r_blk_bytes = r_blk;
+        a.g_tile_bytes = g_tile;
+        a.g_box_bytes = (uint32_t)(TH + a.halo) * P * 128;
+        a.stage_bytes = stage;
+      }
+    }
+  }
+  if (!found) return false;
+  a.tiles_x = (Wo + a.TW - 1) / a.TW;
+  a.tiles_y = (Ho + a.TH - 1) / a.TH;
+  int stages = (int)((kWgSmemBudget - 1024) / a.stage_bytes);
+  if (stages > kWgMaxStages) stages = kWgMaxStages;
+  a.stages = stages;
+  const long long tiles = (long long)a.tiles_x * a.tiles_y * n_img;
+  const long long base_items = (long long)a.m_blks * a.n_blks * a.tap_groups;
+  long long splits = (2LL * wg_sms() + base_items - 1) / base_items;
+  if (splits > tiles) splits = tiles;
+  if (splits < 1) splits = 1;
+  // keep the fp32 partials bounded (<= 256 MiB)
+  const long long per_split = (long long)taps * a.m_pad * a.n_pad * 4;
+  while (splits > 1 && splits * per_split > (256LL << 20)) --splits;
+  a.splits = (int)splits;
+  pl->ws_bytes = (size_t)splits * per_split;
+  pl->smem_bytes = (uint32_t)a.stages * a.stage_bytes + 1024 + 256;
+  const long long items = base_items * splits;
+  pl->grid = (int)(items < wg_sms() ? items : wg_sms());
+  return true;
+}
+
+static int wg_map(CUtensorMap* m, const b200_view& v, int bw, int bh) {
+  uint64_t dims[4] = {(uint64_t)v.c, (uint64_t)v.w, (uint64_t)v.h, (uint64_t)v.n};
+  uint64_t strides[3] = {(uint64_t)v.stride_w * 2, (uint64_t)v.stride_h * 2,
+                         (uint64_t)(v.n > 1 ? v.stride_n : (int64_t)v.stride_h * v.h) * 2};
+  uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, 1};
+  return make_tmap_bf16(m, v.ptr, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+static int wg_launch(const WgMaps& maps, WgPlan& pl, float* dw, int c_src0, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!ws || ws_bytes < pl.ws_bytes) return fail(-1, "wgrad (tcgen05): workspace too small (%zu < %zu)", ws_bytes, pl.ws_bytes);
+  pl.a.ws = (float*)ws;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kWgSmemBudget + 2048);
+    if (e != cudaSuccess) return fail((int)e, "wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_done = true;
+  }
+  wgrad_umma_kernel<<<pl.grid, kWgThreads, pl.smem_bytes, st>>>(maps, pl.a);
+  int r = check_launch("wgrad_umma");
+  if (r) return r;
+  const long long outs = (long long)pl.a.m_total * pl.a.n_total;
+  wgrad_umma_reduce_kernel<<<(unsigned)((outs + 255) / 256), 256, 0, st>>>(pl.a.ws, pl.a.splits, pl.a.taps, pl.a.m_total,
+                                                                           pl.a.n_total, pl.a.m_pad, pl.a.n_pad, c_src0,
+                                                                           pl.a.n_blks0, dw);
+  return check_launch("wgrad_umma_reduce");
+}
+
+static int conv_cin(const b200_conv_wgrad_params* p) {
+  int c = 0;
+  for (int i = 0; i < p->num_src; ++i) c += p->src[i].c;
+  return c;
+}
+
+bool umma_conv_wgrad_ok(const b200_conv_wgrad_params* p) {
+  if (!wg_device_ok()) return false;
+  if (!wg_aligned(p->dz)) return false;
+  for (int i = 0; i < p->num_src; ++i)
+    if (!wg_aligned(p->src[i])) return false;
+  if (p->num_src == 2 && p->src[0].c % 8 != 0) return false;
+  WgPlan pl;
+  return wg_make_plan(0, p->dz.h, p->dz.w, p->dz.n, p->dz.c, conv_cin(p), p->src[0].c, p->taps, p->pad, &pl);
+}
+
+size_t umma_conv_wgrad_workspace(const b200_conv_wgrad_params* p) {
+  WgPlan pl;
+  if (!wg_make_plan(0, p->dz.h, p->dz.w, p->dz.n, p->dz.c, conv_cin(p), p->src[0].c, p->taps, p->pad, &pl)) return 0;
+  return pl.ws_bytes + reduce_workspace_bytes(p->dz.c, 1);
+}
+
+int umma_conv_wgrad(const b200_conv_wgrad_params* p, void* ws, size_t ws_bytes, cudaStream_t st) {
+  WgPlan pl;
+  if (!wg_make_plan(0, p->dz.h, p->dz.w, p->dz.n, p->dz.c, conv_cin(p), p->src[0].c, p->taps, p->pad, &pl))
+    return fail(-1, "conv_wgrad: no plan");
+  WgMaps maps;
+  int r = wg_map(&maps.r, p->dz, pl.a.TW, 1);
+  if (r) return fail(r, "conv_wgrad: tensor map for dz failed (%d)", r);
+  for (int i = 0; i < p->num_src; ++i) {
+    r = wg_map(&maps.g[i], p->src[i], pl.a.P, pl.a.TH + pl.a.halo);
+    if (r) return fail(r, "conv_wgrad: tensor map for src[%d] failed (%d)", i, r);
+  }
+  const size_t need = pl.ws_bytes + (p->db_f32 ? reduce_workspace_bytes(p->dz.c, 1) : 0);
+  if (ws_bytes < need) return fail(-1, "conv_wgrad (tcgen05): workspace too small (%zu < %zu)", ws_bytes, need);
+  r = wg_launch(maps, pl, p->dw_f32, p->src[0].c, ws, ws_bytes, st);
+  if (r) return r;
+  if (p->db_f32) return bias_grad(p->dz, p->db_f32, (char*)ws + pl.ws_bytes, st);
+  return 0;
+}
+
+// ConvTranspose2d: row operand = x (M = cin), gathered operands = the four stride-2 sub-lattices of dy (N = cout)
+static b200_view wg_quadrant(const b200_view& big, int ab) {
+  b200_view q = big;
+  q.ptr = (char*)big.ptr + ((int64_t)(ab >> 1) * big.stride_h + (int64_t)(ab & 1) * big.stride_w) * 2;
+  q.h = big.h / 2;
+  q.w = big.w / 2;
+  q.stride_h = big.stride_h * 2;
+  q.stride_w = big.stride_w * 2;
+  return q;
+}
+
+bool umma_convt_wgrad_ok(const b200_convt_wgrad_params* p) {
+  if (!wg_device_ok()) return false;
+  if (!wg_aligned(p->x) || !wg_aligned(p->dy)) return false;
+  WgPlan pl;
+  return wg_make_plan(1, p->x.h, p->x.w, p->x.n, p->x.c, p->dy.c, p->dy.c, 4, 0, &pl);
+}
+
+size_t umma_convt_wgrad_workspace(const b200_convt_wgrad_params* p) {
+  WgPlan pl;
+  if (!wg_make_plan(1, p->x.h, p->x.w, p->x.n, p->x.c, p->dy.c, p->dy.c, 4, 0, &pl)) return 0;
+  return pl.ws_bytes + reduce_workspace_bytes(p->dy.c, 1);
+}
+
+int umma_convt_wgrad(const b200_convt_wgrad_params* p, void* ws, size_t ws_bytes, cudaStream_t st) {
+  WgPlan pl;
+  if (!wg_make_plan(1, p->x.h, p->x.w, p->x.n, p->x.c, p->dy.c, p->dy.c, 4, 0, &pl))
+    return fail(-1, "convt_wgrad: no plan");
+  WgMaps maps;
+  int r = wg_map(&maps.r, p->x, pl.a.TW, 1);
+  if (r) return fail(r, "convt_wgrad: tensor map for x failed (%d)", r);
+  for (int ab = 0; ab < 4; ++ab) {
+    r = wg_map(&maps.g[ab], wg_quadrant(p->dy, ab), pl.a.P, pl.a.TH);
+    if (r) return fail(r, "convt_wgrad: tensor map for dy sub-lattice %d failed (%d)", ab, r);
+  }
+  const size_t need = pl.ws_bytes + (p->db_f32 ? reduce_workspace_bytes(p->dy.c, 1) : 0);
+  if (ws_bytes < need) return fail(-1, "convt_wgrad (tcgen05): workspace too small (%zu < %zu)", ws_bytes, need);
+  r = wg_launch(maps, pl, p->dw_f32, p->dy.c, ws, ws_bytes, st);
+  if (r) return r;
+  if (p->db_f32) return bias_grad(p->dy, p->db_f32, (char*)ws + pl.ws_bytes, st);
+  return 0;
+}
+
 }  // namespace b200
