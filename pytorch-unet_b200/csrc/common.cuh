@@ -60,22 +60,25 @@ __device__ __forceinline__ float bf2f(bf16 v) { return __bfloat162float(v); }
 __device__ __forceinline__ bf16 f2bf(float v) { return __float2bfloat16_rn(v); }
 
 // 8 bf16 <-> 8 floats through one 16-byte access
-struct __align__(16) bf16x8 {
-  __nv_bfloat162 v[4];
-};
-__device__ __forceinline__ void unpack8(const bf16x8& p, float (&f)[8]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float2 t = __bfloat1622float2(p.v[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
+// (a plain uint4 so that the compiler emits one LDG.128 / STG.128; a struct of four bfloat162 is copied word by word)
+typedef uint4 bf16x8;
+__device__ __forceinline__ float2 bf2x_to_f2(uint32_t w) {
+  // bf16 -> fp32 is a 16-bit shift
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t f2_to_bf2x(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void unpack8(const bf16x8 p, float (&f)[8]) {
+  float2 t;
+  t = bf2x_to_f2(p.x); f[0] = t.x; f[1] = t.y;
+  t = bf2x_to_f2(p.y); f[2] = t.x; f[3] = t.y;
+  t = bf2x_to_f2(p.z); f[4] = t.x; f[5] = t.y;
+  t = bf2x_to_f2(p.w); f[6] = t.x; f[7] = t.y;
 }
 __device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
-  bf16x8 p;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-  return p;
+  return make_uint4(f2_to_bf2x(f[0], f[1]), f2_to_bf2x(f[2], f[3]), f2_to_bf2x(f[4], f[5]), f2_to_bf2x(f[6], f[7]));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

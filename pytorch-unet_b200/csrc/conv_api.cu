@@ -103,7 +103,9 @@ int b200unet_conv_fwd(const b200_conv_fwd_params* p, void* stream) {
   int r = check_conv_fwd(p), impl;
   if (r) return r;
   if ((r = resolve(p, umma_conv_fwd_ok, "conv_fwd", &impl))) return r;
-  return impl == B200_IMPL_UMMA ? umma_conv_fwd(p, as_stream(stream)) : direct_conv_fwd(p, as_stream(stream));
+  if (impl == B200_IMPL_UMMA) return umma_conv_fwd(p, as_stream(stream));
+  if (p->impl == B200_IMPL_AUTO && smallc_conv_fwd_ok(p)) return smallc_conv_fwd(p, as_stream(stream));
+  return direct_conv_fwd(p, as_stream(stream));
 }
 
 int b200unet_conv_dgrad(const b200_conv_dgrad_params* p, void* stream) {
@@ -119,15 +121,18 @@ size_t b200unet_conv_wgrad_workspace_bytes(const b200_conv_wgrad_params* p) {
   const size_t u = umma_conv_wgrad_ok(p) ? umma_conv_wgrad_workspace(p) : 0;
   if (p->impl == B200_IMPL_DIRECT) return d;
   if (p->impl == B200_IMPL_UMMA) return u;
-  return umma_conv_wgrad_ok(p) ? u : d;
+  if (umma_conv_wgrad_ok(p)) return u;
+  return smallc_conv_wgrad_ok(p) ? smallc_conv_wgrad_workspace(p) : d;
 }
 
 int b200unet_conv_wgrad(const b200_conv_wgrad_params* p, void* workspace, size_t workspace_bytes, void* stream) {
   int r = check_conv_wgrad(p), impl;
   if (r) return r;
   if ((r = resolve(p, umma_conv_wgrad_ok, "conv_wgrad", &impl))) return r;
-  return impl == B200_IMPL_UMMA ? umma_conv_wgrad(p, workspace, workspace_bytes, as_stream(stream))
-                                : direct_conv_wgrad(p, workspace, workspace_bytes, as_stream(stream));
+  if (impl == B200_IMPL_UMMA) return umma_conv_wgrad(p, workspace, workspace_bytes, as_stream(stream));
+  if (p->impl == B200_IMPL_AUTO && smallc_conv_wgrad_ok(p))
+    return smallc_conv_wgrad(p, workspace, workspace_bytes, as_stream(stream));
+  return direct_conv_wgrad(p, workspace, workspace_bytes, as_stream(stream));
 }
 
 int b200unet_convt_fwd(const b200_convt_fwd_params* p, void* stream) {

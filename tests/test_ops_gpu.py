@@ -182,6 +182,11 @@ CONV_CASES = [
     (1, (256,), 128, 6, 6, 1, 0),
     (3, (64,), 64, 40, 70, 3, 0),
     (1, (512,), 512, 10, 12, 3, 0),
+    # first-layer kernels (1..4 input channels, cout % 16 == 0)
+    (2, (3,), 32, 19, 23, 3, 1),
+    (1, (2,), 16, 9, 30, 3, 0),
+    (1, (4,), 128, 12, 13, 3, 1),
+    (3, (1,), 64, 33, 41, 3, 1),
 ]
 
 
