@@ -52,14 +52,15 @@ struct WgItem {
   int tile0, tile1;
 };
 
-__device__ __forceinline__ WgItem decode_item(const WgArgs& a, int item) {
+// A CTA runs both tap groups of a (split, N block, M block) back to back, so that every CTA gets the same amount of
+// MMA work (5 + 4 taps) and the second pass re-reads tiles that are still warm in L2.
+__device__ __forceinline__ WgItem decode_item(const WgArgs& a, int item, int grp) {
   WgItem w;
   w.mb = item % a.m_blks;
   item /= a.m_blks;
   w.nb = item % a.n_blks;
-  item /= a.n_blks;
-  w.grp = item % a.tap_groups;
-  w.split = item / a.tap_groups;
+  w.split = item / a.n_blks;
+  w.grp = grp;
   const int per = (a.taps + a.tap_groups - 1) / a.tap_groups;
   w.tap0 = w.grp * per;
   w.ntap = min(per, a.taps - w.tap0);
@@ -81,7 +82,7 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_items = a.m_blks * a.n_blks * a.tap_groups * a.splits;
+  const int total_items = a.m_blks * a.n_blks * a.splits;
   const int g_tiles = a.mode == 1 ? a.taps : 1;
 
   // zero the whole pipeline once: halo columns / tail rows of the R tiles and the unused tail of the G tiles must
@@ -112,8 +113,9 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
       tma_prefetch_desc(&maps.r);
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const WgItem w = decode_item(a, item);
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x)
+      for (int grp = 0; grp < a.tap_groups; ++grp) {
+        const WgItem w = decode_item(a, item, grp);
         // gathered-operand source of this N block
         int gsrc = 0, gc0 = w.nb * 64;
         if (a.mode == 0 && w.nb >= a.n_blks0) {
@@ -157,8 +159,9 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
       uint32_t phase = 0;
       int it = 0;
       const int ksteps = a.kt_rows / 16;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
-        const WgItem w = decode_item(a, item);
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x)
+      for (int grp = 0; grp < a.tap_groups; ++grp, ++it) {
+        const WgItem w = decode_item(a, item, grp);
         mbar_wait(t_empty, (it & 1) ^ 1);
         tc_fence_after_sync();
         bool first = true;
@@ -194,8 +197,9 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
     // epilogue: TMEM -> fp32 partials ws[split][tap][m][n]
     const int quarter = warp & 3;
     int it = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
-      const WgItem w = decode_item(a, item);
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x)
+    for (int grp = 0; grp < a.tap_groups; ++grp, ++it) {
+      const WgItem w = decode_item(a, item, grp);
       mbar_wait(t_full, it & 1);
       tc_fence_after_sync();
       const int m = w.mb * 128 + quarter * 32 + lane;
@@ -304,9 +308,13 @@ static bool wg_make_plan(int mode, int Ho, int Wo, int n_img, int m_total, int n
       const uint32_t g_rows = (uint32_t)max((TH + a.halo) * P, kt + a.halo * P + a.halo);
       const uint32_t g_tile = (g_rows * 128 + 1023) & ~1023u;
       const uint32_t stage = 2 * r_blk + g_tiles * g_tile;
-      if (2 * stage + 1024 > kWgSmemBudget) continue;
+      if (3 * stage + 1024 > kWgSmemBudget) continue;  // >= 3 stages: the kernel is fed from L2, latency must hide
       const long long tiles = (long long)((Wo + TW - 1) / TW) * ((Ho + TH - 1) / TH) * n_img;
-      const double cost = (double)tiles * (kt + 24);
+      // per tile: MMA time ~ taps-per-group * K steps * ~48 cycles (shared-memory-bound N = 64 MMA), load time ~ bytes
+      // moved L2 -> SMEM at ~32 B/cycle/SM; whichever is larger, plus a fixed per-tile cost
+      const double t_mma = (taps == 9 ? 4.5 : taps) * (kt / 16) * 48.0;
+      const double t_load = ((double)a.r_blocks * TH * TW * 128 + (double)g_tiles * (TH + a.halo) * P * 128) / 32.0;
+      const double cost = (double)tiles * ((t_mma > t_load ? t_mma : t_load) + 300.0);
       if (cost < best) {
         best = cost;
         found = true;
@@ -328,10 +336,22 @@ static bool wg_make_plan(int mode, int Ho, int Wo, int n_img, int m_total, int n
   if (stages > kWgMaxStages) stages = kWgMaxStages;
   a.stages = stages;
   const long long tiles = (long long)a.tiles_x * a.tiles_y * n_img;
-  const long long base_items = (long long)a.m_blks * a.n_blks * a.tap_groups;
-  long long splits = (2LL * wg_sms() + base_items - 1) / base_items;
-  if (splits > tiles) splits = tiles;
-  if (splits < 1) splits = 1;
+  const long long base_items = (long long)a.m_blks * a.n_blks;
+  // pixel splits: make the number of work items fill whole waves of the persistent grid
+  long long splits = 1;
+  double best_eff = 0.0;
+  for (int k = 1; k <= 3; ++k) {
+    long long sp = (long long)wg_sms() * k / base_items;
+    if (sp < 1) sp = 1;
+    if (sp > tiles) sp = tiles;
+    const long long items = base_items * sp;
+    const long long waves = (items + wg_sms() - 1) / wg_sms();
+    const double eff = (double)items / (double)(waves * wg_sms());
+    if (eff > best_eff + 0.03) {
+      best_eff = eff;
+      splits = sp;
+    }
+  }
   // keep the fp32 partials bounded (<= 256 MiB)
   const long long per_split = (long long)taps * a.m_pad * a.n_pad * 4;
   while (splits > 1 && splits * per_split > (256LL << 20)) --splits;
