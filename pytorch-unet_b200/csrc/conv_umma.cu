@@ -165,54 +165,59 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       }
     }
   } else if (warp == 2) {
-    // ================= MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
-      constexpr uint64_t desc_hi = umma_desc_hi_sw128(16, 1024);
-      int astage = 0, bstage = 0;
-      uint32_t aphase = 0, bphase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int buf = it % NBUF;
-        mbar_wait(&t_empty[buf], ((it / NBUF) & 1) ^ 1);
-        tc_fence_after_sync();
-        const uint32_t acc = tmem_base + buf * (MB * BN);
-        bool first = true;
-        for (int s = 0; s < a.num_a; ++s) {
-          for (int c0 = 0; c0 < a.a_c[s]; c0 += 64) {
-            mbar_wait(&a_full[astage], aphase);
-            const uint32_t a_base = smem_u32(sA + astage * a.a_stage_bytes);
-            for (int tap = 0; tap < a.taps; ++tap) {
-              mbar_wait(&b_full[bstage], bphase);
-              tc_fence_after_sync();
-              const uint32_t b_base = smem_u32(sB + bstage * B_STAGE_BYTES);
-              const int r = tap / a.kx, sx = tap - r * a.kx;
-              const uint32_t a_tap = a_base + (uint32_t)(r * a.P + sx) * 128;
+    // ================= MMA issuer.  The whole warp runs the control flow so that addresses and descriptors are
+    // warp-uniform (uniform registers; a lane-0 branch costs an ELECT + 4 R2UR per MMA and halves the issue rate at
+    // N = 64); one elected lane issues the tcgen05 instructions.
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+    constexpr uint64_t desc_hi = umma_desc_hi_sw128(16, 1024);
+    int astage = 0, bstage = 0;
+    uint32_t aphase = 0, bphase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it % NBUF;
+      mbar_wait(&t_empty[buf], ((it / NBUF) & 1) ^ 1);
+      tc_fence_after_sync();
+      const uint32_t acc = tmem_base + buf * (MB * BN);
+      uint32_t accum = 0;
+      for (int s = 0; s < a.num_a; ++s) {
+        for (int c0 = 0; c0 < a.a_c[s]; c0 += 64) {
+          mbar_wait(&a_full[astage], aphase);
+          const uint32_t a_base = smem_u32(sA + astage * a.a_stage_bytes);
+          for (int tap = 0; tap < a.taps; ++tap) {
+            mbar_wait(&b_full[bstage], bphase);
+            tc_fence_after_sync();
+            const int r = tap / a.kx, sx = tap - r * a.kx;
+            const uint64_t a_desc = umma_desc(desc_hi, a_base + (uint32_t)(r * a.P + sx) * 128);
+            const uint64_t b_desc = umma_desc(desc_hi, smem_u32(sB + bstage * B_STAGE_BYTES));
+            if (elect_one()) {
 #pragma unroll
               for (int mb = 0; mb < MB; ++mb) {
+                // M-block m starts 128 rows (16 KiB -> 1024 in the >>4 address field) further; K step = 32 B -> 2.
+                // The first MMA into each M-block's accumulator overwrites, everything after accumulates.
+                umma_bf16(acc + mb * BN, a_desc + (uint64_t)mb * 1024, b_desc, idesc, accum);
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                  // the first MMA into each M-block's accumulator overwrites, everything after accumulates
-                  umma_bf16(acc + mb * BN, umma_desc(desc_hi, a_tap + mb * (128 * 128) + kk * 32),
-                            umma_desc(desc_hi, b_base + kk * 32), idesc, (first && kk == 0) ? 0u : 1u);
-                }
+                for (int kk = 1; kk < 4; ++kk)
+                  umma_bf16(acc + mb * BN, a_desc + (uint64_t)(mb * 1024 + kk * 2), b_desc + (uint64_t)(kk * 2), idesc, 1u);
               }
-              first = false;
               umma_commit(&b_empty[bstage]);
-              if (++bstage == a.nb_stages) {
-                bstage = 0;
-                bphase ^= 1;
-              }
             }
-            umma_commit(&a_empty[astage]);
-            if (++astage == kNA) {
-              astage = 0;
-              aphase ^= 1;
+            __syncwarp();
+            accum = 1;
+            if (++bstage == a.nb_stages) {
+              bstage = 0;
+              bphase ^= 1;
             }
           }
+          if (elect_one()) umma_commit(&a_empty[astage]);
+          __syncwarp();
+          if (++astage == kNA) {
+            astage = 0;
+            aphase ^= 1;
+          }
         }
-        umma_commit(&t_full[buf]);
       }
+      if (elect_one()) umma_commit(&t_full[buf]);
+      __syncwarp();
     }
   } else {
     // ================= epilogue: 4 warps, warp w owns TMEM lanes 32*(w%4) .. +31

@@ -1,5 +1,6 @@
 // tcgen05 backward-weights kernel for the convolution family:
 //   conv 3x3 / 1x1:   dW[o][c][r][s] = sum_{n,y,x} dz[n,y,x,o] * x[n,y+r-pad,x+s-pad,c]      (two concatenated sources)
+//                     db[o]          = sum_{n,y,x} dz[n,y,x,o]
 //   ConvTranspose2d:  dW[c][o][a][b] = sum_{n,i,j} x[n,i,j,c] * dy[n,2i+a,2j+b,o]
 //
 // GEMM view (per filter tap): D_tap[M = row-operand channels, N = gathered-operand channels] += R^T * G_tap, with the
@@ -8,12 +9,17 @@
 //   R tile ("row operand": dz, or x for the transposed conv): TH x TW pixels stored with pitch P = TW + halo; the halo
 //     columns and the rows past TH*P stay zero (zero-filled once, TMA never touches them), so they add nothing.
 //   G tile ("gathered operand": x, or the four stride-2 sub-lattices of dy): (TH+halo) x P pixels, loaded once; tap
-//     (r, s) is the same buffer read through a descriptor advanced by r*P + s rows — the same shifted-descriptor
-//     trick as the forward kernel, now on the K axis.
-// Accumulators: one [128 x 64] fp32 block per tap in TMEM; 9 taps x 64 columns do not fit in 512, so a 3x3 runs as two
-// tap groups (5 + 4) that are separate work items.  Work item = (pixel split, tap group, 64-channel N block, 128-channel
-// M block); partial sums go to a fp32 workspace [split][tap][M][N] and a second kernel reduces the splits in a fixed
-// order and writes the state_dict layout, so results are run-to-run reproducible.
+//     (r, s) is the same buffer read through a descriptor advanced by r*P + s rows — the shifted-descriptor trick of
+//     the forward kernel, now on the K axis.
+// Accumulators: one [128 x 64] fp32 block per tap in TMEM.  9 taps x 64 columns do not fit in 512, so
+//   * Cout >= 128: a 3x3 runs as two tap groups (5 + 4) executed back to back by the same CTA;
+//   * Cout <= 64 ("paired" mode): the second 64-lane half of the M = 128 MMA would be idle, so it is given the SAME dz
+//     tile stored one pixel row later.  One MMA with gathered shift sigma then yields tap sigma+1 on lanes 0..63 and
+//     tap sigma on lanes 64..127: the nine taps need 6 MMAs (sigma = rP and rP+2) and 384 columns — one pass.
+// Bias gradient: one extra N = 16 MMA per K step against a block of ones (column sums of dz on the tensor core).
+// Work item = (pixel split, 64-channel N block, 128-channel M block); fp32 partials [split][tap][M][N] (+ [split][M]
+// for the bias); a second kernel reduces the splits in a fixed order and writes the state_dict layout, so results are
+// run-to-run reproducible.
 #include "chan_reduce.cuh"
 #include "conv_impl.h"
 #include "ptx.cuh"
@@ -24,6 +30,8 @@ namespace b200 {
 constexpr int kWgThreads = 192;  // warp 0 producer, warp 1 MMA, warps 2..5 epilogue
 constexpr int kWgMaxStages = 4;
 constexpr uint32_t kWgSmemBudget = 200 * 1024;
+constexpr uint32_t kWgOnesBytes = 2048;  // 16 K rows x 128 B of bf16 1.0
+constexpr int kWgBiasCol = 448;          // TMEM column of the bias accumulator (taps use at most 6 * 64 = 384)
 
 struct WgMaps {
   CUtensorMap r;     // row operand
@@ -31,16 +39,19 @@ struct WgMaps {
 };
 
 struct WgArgs {
-  int mode;  // 0 = conv (taps share one G tile), 1 = convT (one G tile per tap)
+  int mode;    // 0 = conv (taps share one G tile), 1 = convT (one G tile per tap)
+  int paired;  // conv 3x3 with <= 64 row channels: two taps per MMA (see header)
+  int bias;    // accumulate column sums of the row operand (conv bias gradient)
   int m_total, n_total;
-  int g_c[2];       // conv: channels per concat source
-  int n_blks0;      // conv: number of 64-blocks of source 0
+  int g_c[2];   // conv: channels per concat source
+  int n_blks0;  // conv: number of 64-blocks of source 0
   int taps, kx, halo, pad;
   int P, TH, TW, kt_rows;
   int tiles_x, tiles_y, n_img;
   int m_blks, n_blks, tap_groups, splits;
   int m_pad, n_pad;
   float* ws;
+  float* ws_bias;  // [splits][m_pad]
   uint32_t r_blk_bytes, g_tile_bytes, g_box_bytes, stage_bytes;
   int stages;
   int r_blocks;  // 64-channel blocks of the row operand actually loaded (1 or 2)
@@ -48,7 +59,7 @@ struct WgArgs {
 
 struct WgItem {
   int split, grp, nb, mb;
-  int tap0, ntap;
+  int tap0, ntap;  // unpaired: taps of this group; paired: ntap = number of MMA groups (6)
   int tile0, tile1;
 };
 
@@ -61,9 +72,14 @@ __device__ __forceinline__ WgItem decode_item(const WgArgs& a, int item, int grp
   w.nb = item % a.n_blks;
   w.split = item / a.n_blks;
   w.grp = grp;
-  const int per = (a.taps + a.tap_groups - 1) / a.tap_groups;
-  w.tap0 = w.grp * per;
-  w.ntap = min(per, a.taps - w.tap0);
+  if (a.paired) {
+    w.tap0 = 0;
+    w.ntap = 6;
+  } else {
+    const int per = (a.taps + a.tap_groups - 1) / a.tap_groups;
+    w.tap0 = w.grp * per;
+    w.ntap = min(per, a.taps - w.tap0);
+  }
   const long long total = (long long)a.tiles_x * a.tiles_y * a.n_img;
   w.tile0 = (int)(total * w.split / a.splits);
   w.tile1 = (int)(total * (w.split + 1) / a.splits);
@@ -74,7 +90,8 @@ __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (uint32_t)a.stages * a.stage_bytes);
+  uint8_t* ones = smem + (uint32_t)a.stages * a.stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ones + kWgOnesBytes);
   uint64_t* full = bars;
   uint64_t* empty = full + kWgMaxStages;
   uint64_t* t_full = empty + kWgMaxStages;
@@ -91,6 +108,9 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
     uint4* p = reinterpret_cast<uint4*>(smem);
     const uint32_t n16 = (uint32_t)a.stages * a.stage_bytes / 16;
     for (uint32_t i = threadIdx.x; i < n16; i += kWgThreads) p[i] = make_uint4(0, 0, 0, 0);
+    uint4* o = reinterpret_cast<uint4*>(ones);
+    for (uint32_t i = threadIdx.x; i < kWgOnesBytes / 16; i += kWgThreads)
+      o[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);  // bf16 1.0 pairs
   }
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWgMaxStages; ++i) {
@@ -113,144 +133,205 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
       tma_prefetch_desc(&maps.r);
       int stage = 0;
       uint32_t phase = 0;
+      const int r_loads = a.paired ? 2 : a.r_blocks;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x)
-      for (int grp = 0; grp < a.tap_groups; ++grp) {
-        const WgItem w = decode_item(a, item, grp);
-        // gathered-operand source of this N block
-        int gsrc = 0, gc0 = w.nb * 64;
-        if (a.mode == 0 && w.nb >= a.n_blks0) {
-          gsrc = 1;
-          gc0 = (w.nb - a.n_blks0) * 64;
-        }
-        for (int tile = w.tile0; tile < w.tile1; ++tile) {
-          const int txi = tile % a.tiles_x;
-          const int tyi = (tile / a.tiles_x) % a.tiles_y;
-          const int n = tile / (a.tiles_x * a.tiles_y);
-          const int y0 = tyi * a.TH, x0 = txi * a.TW;
-          uint8_t* st = smem + stage * a.stage_bytes;
-          mbar_wait(&empty[stage], phase ^ 1);
-          const uint32_t tx_bytes = (uint32_t)a.r_blocks * a.TH * a.TW * 128 + (uint32_t)g_tiles * a.g_box_bytes;
-          mbar_arrive_expect_tx(&full[stage], tx_bytes);
-          // R tile: one TMA per tile row so that rows land with pitch P (halo columns stay zero)
-          for (int rb = 0; rb < a.r_blocks; ++rb)
-            for (int ty = 0; ty < a.TH; ++ty)
-              tma_load_4d(&maps.r, &full[stage], st + rb * a.r_blk_bytes + (uint32_t)(ty * a.P) * 128,
-                          w.mb * 128 + rb * 64, x0, y0 + ty, n);
-          uint8_t* gt = st + 2 * a.r_blk_bytes;
-          if (a.mode == 0) {
-            tma_load_4d(&maps.g[gsrc], &full[stage], gt, gc0, x0 - a.pad, y0 - a.pad, n);
-          } else {
-            for (int t = 0; t < a.taps; ++t)
-              tma_load_4d(&maps.g[t], &full[stage], gt + t * a.g_tile_bytes, gc0, x0, y0, n);
+        for (int grp = 0; grp < a.tap_groups; ++grp) {
+          const WgItem w = decode_item(a, item, grp);
+          // gathered-operand source of this N block
+          int gsrc = 0, gc0 = w.nb * 64;
+          if (a.mode == 0 && w.nb >= a.n_blks0) {
+            gsrc = 1;
+            gc0 = (w.nb - a.n_blks0) * 64;
           }
-          if (++stage == a.stages) {
-            stage = 0;
-            phase ^= 1;
+          for (int tile = w.tile0; tile < w.tile1; ++tile) {
+            const int txi = tile % a.tiles_x;
+            const int tyi = (tile / a.tiles_x) % a.tiles_y;
+            const int n = tile / (a.tiles_x * a.tiles_y);
+            const int y0 = tyi * a.TH, x0 = txi * a.TW;
+            uint8_t* st = smem + stage * a.stage_bytes;
+            mbar_wait(&empty[stage], phase ^ 1);
+            const uint32_t tx_bytes = (uint32_t)r_loads * a.TH * a.TW * 128 + (uint32_t)g_tiles * a.g_box_bytes;
+            mbar_arrive_expect_tx(&full[stage], tx_bytes);
+            // R tile: one TMA per tile row so that rows land with pitch P (halo columns stay zero).  Paired mode:
+            // block 0 holds the tile one row later (row q+1 = pixel q), block 1 holds it in place.
+            for (int rb = 0; rb < r_loads; ++rb) {
+              const int ch = a.paired ? w.mb * 128 : w.mb * 128 + rb * 64;
+              const int row_off = (a.paired && rb == 0) ? 1 : 0;
+              for (int ty = 0; ty < a.TH; ++ty)
+                tma_load_4d(&maps.r, &full[stage], st + rb * a.r_blk_bytes + (uint32_t)(ty * a.P + row_off) * 128, ch, x0,
+                            y0 + ty, n);
+            }
+            uint8_t* gt = st + 2 * a.r_blk_bytes;
+            if (a.mode == 0) {
+              tma_load_4d(&maps.g[gsrc], &full[stage], gt, gc0, x0 - a.pad, y0 - a.pad, n);
+            } else {
+              for (int t = 0; t < a.taps; ++t)
+                tma_load_4d(&maps.g[t], &full[stage], gt + t * a.g_tile_bytes, gc0, x0, y0, n);
+            }
+            if (++stage == a.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
         }
-      }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);  // both operands MN-major
-      const uint64_t hi_r = umma_desc_hi_sw128(a.r_blk_bytes, 1024);
-      const uint64_t hi_g = umma_desc_hi_sw128(a.r_blk_bytes, 1024);  // N = 64: a single block, LBO unused
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      const int ksteps = a.kt_rows / 16;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x)
+    // The whole warp runs the control flow so that every address / descriptor is warp-uniform (lives in uniform
+    // registers, no per-MMA R2UR/ELECT sequences); one elected lane issues the tcgen05 instructions.
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);  // both operands MN-major
+    constexpr uint32_t idesc_bias = umma_idesc_bf16(128, 16, 1, 1);
+    const uint64_t hi_r = umma_desc_hi_sw128(a.r_blk_bytes, 1024);
+    const uint64_t hi_g = umma_desc_hi_sw128(a.r_blk_bytes, 1024);  // N <= 64: a single block, LBO unused
+    const uint64_t ones_desc = umma_desc(hi_g, smem_u32(ones));
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    const int ksteps = a.kt_rows / 16;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x)
       for (int grp = 0; grp < a.tap_groups; ++grp, ++it) {
         const WgItem w = decode_item(a, item, grp);
+        const bool do_bias = a.bias && w.nb == 0 && grp == 0;
         mbar_wait(t_empty, (it & 1) ^ 1);
         tc_fence_after_sync();
-        bool first = true;
+        uint32_t accum = 0;
         for (int tile = w.tile0; tile < w.tile1; ++tile) {
           mbar_wait(&full[stage], phase);
           tc_fence_after_sync();
           const uint32_t r_base = smem_u32(smem + stage * a.stage_bytes);
           const uint32_t g_base = r_base + 2 * a.r_blk_bytes;
-          for (int j = 0; j < w.ntap; ++j) {
-            const int tap = w.tap0 + j;
-            uint32_t g_tap;
-            if (a.mode == 0) {
-              const int r = tap / a.kx, sx = tap - r * a.kx;
-              g_tap = g_base + (uint32_t)(r * a.P + sx) * 128;
-            } else {
-              g_tap = g_base + tap * a.g_tile_bytes;
+          const uint64_t r_desc = umma_desc(hi_r, r_base);
+          if (elect_one()) {
+            for (int j = 0; j < w.ntap; ++j) {
+              uint32_t g_tap;
+              if (a.paired) {
+                const int r = j >> 1, sx = (j & 1) * 2;  // sigma = r*P + {0, 2}
+                g_tap = g_base + (uint32_t)(r * a.P + sx) * 128;
+              } else if (a.mode == 0) {
+                const int tap = w.tap0 + j;
+                const int r = tap / a.kx, sx = tap - r * a.kx;
+                g_tap = g_base + (uint32_t)(r * a.P + sx) * 128;
+              } else {
+                g_tap = g_base + (w.tap0 + j) * a.g_tile_bytes;
+              }
+              const uint64_t g_desc = umma_desc(hi_g, g_tap);
+              const uint32_t d = tmem_base + j * 64;
+              // one K step = 16 pixel rows = 2048 B = 128 in the descriptor's (address >> 4) field
+              umma_bf16(d, r_desc, g_desc, idesc, accum);
+#pragma unroll 4
+              for (int k = 1; k < ksteps; ++k) umma_bf16(d, r_desc + (uint64_t)k * 128, g_desc + (uint64_t)k * 128, idesc, 1u);
             }
-            for (int k = 0; k < ksteps; ++k)
-              umma_bf16(tmem_base + j * 64, umma_desc(hi_r, r_base + k * 2048), umma_desc(hi_g, g_tap + k * 2048), idesc,
-                        (first && k == 0) ? 0u : 1u);
+            if (do_bias) {
+              umma_bf16(tmem_base + kWgBiasCol, r_desc, ones_desc, idesc_bias, accum);
+#pragma unroll 4
+              for (int k = 1; k < ksteps; ++k)
+                umma_bf16(tmem_base + kWgBiasCol, r_desc + (uint64_t)k * 128, ones_desc, idesc_bias, 1u);
+            }
+            umma_commit(&empty[stage]);
           }
-          first = false;
-          umma_commit(&empty[stage]);
+          __syncwarp();
+          accum = 1;
           if (++stage == a.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(t_full);
+        if (elect_one()) umma_commit(t_full);
+        __syncwarp();
       }
-    }
   } else {
     // epilogue: TMEM -> fp32 partials ws[split][tap][m][n]
     const int quarter = warp & 3;
     int it = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x)
-    for (int grp = 0; grp < a.tap_groups; ++grp, ++it) {
-      const WgItem w = decode_item(a, item, grp);
-      mbar_wait(t_full, it & 1);
-      tc_fence_after_sync();
-      const int m = w.mb * 128 + quarter * 32 + lane;
-      const bool empty_item = w.tile1 <= w.tile0;  // no MMA was issued: the accumulator holds stale data
-      for (int j = 0; j < w.ntap; ++j) {
-        const int tap = w.tap0 + j;
-        float* out = a.ws + (((long long)w.split * a.taps + tap) * a.m_pad + m) * a.n_pad + w.nb * 64;
+      for (int grp = 0; grp < a.tap_groups; ++grp, ++it) {
+        const WgItem w = decode_item(a, item, grp);
+        mbar_wait(t_full, it & 1);
+        tc_fence_after_sync();
+        const int row = quarter * 32 + lane;           // TMEM lane = accumulator row
+        const bool empty_item = w.tile1 <= w.tile0;    // no MMA was issued: the accumulator holds stale data
+        for (int j = 0; j < w.ntap; ++j) {
+          int tap, m;
+          bool live = true;
+          if (a.paired) {
+            const int r = j >> 1;
+            if (row < 64) {  // tap sigma + 1: only sigma = rP gives a real tap (r, 1)
+              tap = r * 3 + 1;
+              m = row;
+              live = (j & 1) == 0;
+            } else {         // tap sigma: (r, 0) or (r, 2)
+              tap = r * 3 + (j & 1) * 2;
+              m = row - 64;
+            }
+          } else {
+            tap = w.tap0 + j;
+            m = w.mb * 128 + row;
+          }
+          float* out = a.ws + (((long long)w.split * a.taps + tap) * a.m_pad + m) * a.n_pad + w.nb * 64;
 #pragma unroll 1
-        for (int col0 = 0; col0 < 64; col0 += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_base + j * 64 + col0 + (uint32_t(quarter * 32) << 16), v);
-          tmem_ld_wait();
+          for (int col0 = 0; col0 < 64; col0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + j * 64 + col0 + (uint32_t(quarter * 32) << 16), v);
+            tmem_ld_wait();
+            if (live) {
 #pragma unroll
-          for (int q4 = 0; q4 < 8; ++q4) {
-            float4 f;
-            f.x = empty_item ? 0.f : __uint_as_float(v[q4 * 4 + 0]);
-            f.y = empty_item ? 0.f : __uint_as_float(v[q4 * 4 + 1]);
-            f.z = empty_item ? 0.f : __uint_as_float(v[q4 * 4 + 2]);
-            f.w = empty_item ? 0.f : __uint_as_float(v[q4 * 4 + 3]);
-            *reinterpret_cast<float4*>(out + col0 + q4 * 4) = f;
+              for (int q4 = 0; q4 < 8; ++q4) {
+                float4 f;
+                f.x = empty_item ? 0.f : __uint_as_float(v[q4 * 4 + 0]);
+                f.y = empty_item ? 0.f : __uint_as_float(v[q4 * 4 + 1]);
+                f.z = empty_item ? 0.f : __uint_as_float(v[q4 * 4 + 2]);
+                f.w = empty_item ? 0.f : __uint_as_float(v[q4 * 4 + 3]);
+                *reinterpret_cast<float4*>(out + col0 + q4 * 4) = f;
+              }
+            }
           }
         }
+        if (a.bias && w.nb == 0 && grp == 0) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + kWgBiasCol + (uint32_t(quarter * 32) << 16), v);  // columns 0..15 are the sums
+          tmem_ld_wait();
+          const bool live = !a.paired || row < 64;
+          if (live) a.ws_bias[(long long)w.split * a.m_pad + w.mb * 128 + row] = empty_item ? 0.f : __uint_as_float(v[0]);
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(t_empty);
       }
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(t_empty);
-    }
   }
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
-// dw[(m * n_total + n) * taps + tap] = sum_s ws[s][tap][m][npad(n)]
+// dw[(m * n_total + n) * taps + tap] = sum_s ws[s][tap][m][npad(n)].  Block = one m, 32 consecutive n, all taps: reads
+// are coalesced along n, the transposed result goes through shared memory so that the store is contiguous.
 __global__ void wgrad_umma_reduce_kernel(const float* __restrict__ ws, int splits, int taps, int m_total, int n_total,
-                                         int m_pad, int n_pad, int c_src0, int n_blks0, float* __restrict__ dw) {
-  const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (e >= (long long)m_total * n_total) return;
-  const int n = (int)(e % n_total), m = (int)(e / n_total);
-  const int np = n < c_src0 ? n : n_blks0 * 64 + (n - c_src0);
-  for (int t = 0; t < taps; ++t) {
+                                         int m_pad, int n_pad, int c_src0, int n_blks0, float* __restrict__ dw,
+                                         const float* __restrict__ ws_bias, float* __restrict__ db) {
+  __shared__ float tile[32 * 9];
+  const int m = blockIdx.y;
+  const int n0 = blockIdx.x * 32;
+  const int nl = threadIdx.x & 31, t = threadIdx.x >> 5;
+  const int n = n0 + nl;
+  if (t < taps && n < n_total) {
+    const int np = n < c_src0 ? n : n_blks0 * 64 + (n - c_src0);
     float s = 0.f;
     for (int i = 0; i < splits; ++i) s += ws[(((long long)i * taps + t) * m_pad + m) * n_pad + np];
-    dw[e * taps + t] = s;
+    tile[nl * taps + t] = s;
+  }
+  __syncthreads();
+  const int cnt = min(32, n_total - n0) * taps;
+  for (int j = threadIdx.x; j < cnt; j += blockDim.x) dw[((long long)m * n_total + n0) * taps + j] = tile[j];
+  if (db && blockIdx.x == 0 && threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < splits; ++i) s += ws_bias[(long long)i * m_pad + m];
+    db[m] = s;
   }
 }
 
 // ------------------------------------------------------------------ host side
 struct WgPlan {
   WgArgs a;
-  size_t ws_bytes;
+  size_t ws_bytes, ws_bias_bytes;
   uint32_t smem_bytes;
   int grid;
 };
@@ -274,7 +355,7 @@ static int wg_sms() {
 
 // row operand extent Ho x Wo x n_img; M = row channels, N = gathered channels (per source for conv)
 static bool wg_make_plan(int mode, int Ho, int Wo, int n_img, int m_total, int n_total, int c_src0, int taps, int pad,
-                         WgPlan* pl) {
+                         bool want_bias, WgPlan* pl) {
   WgArgs& a = pl->a;
   a = WgArgs{};
   a.mode = mode;
@@ -291,30 +372,35 @@ static bool wg_make_plan(int mode, int Ho, int Wo, int n_img, int m_total, int n
   a.n_blks = a.n_blks0 + (mode == 0 ? (a.g_c[1] + 63) / 64 : 0);
   a.m_blks = (m_total + 127) / 128;
   a.r_blocks = m_total > 64 ? 2 : 1;
-  a.tap_groups = taps == 9 ? 2 : 1;
+  a.paired = (mode == 0 && taps == 9 && m_total <= 64) ? 1 : 0;
+  a.bias = (want_bias && mode == 0) ? 1 : 0;
+  a.tap_groups = (taps == 9 && !a.paired) ? 2 : 1;
   a.m_pad = a.m_blks * 128;
   a.n_pad = a.n_blks * 64;
   const int g_tiles = mode == 1 ? taps : 1;
-  // tile geometry: kt_rows (multiple of 16) K rows per tile; minimise issued K rows
+  const int r_loads = a.paired ? 2 : a.r_blocks;
+  const double mma_groups = a.paired ? 6.0 : (taps == 9 ? 4.5 : (double)taps);
+  const double passes = a.tap_groups;
+  // tile geometry: kt_rows (multiple of 16) K rows per tile
   double best = 1e30;
   bool found = false;
   for (int kt = 64; kt <= 256; kt += 16) {
     for (int P = a.halo + 1; P <= 256 && P <= Wo + a.halo + 8; ++P) {
       const int TW = P - a.halo;
-      int TH = kt / P;
+      int TH = (kt - a.paired) / P;
       if (TH < 1) break;
       if (TH > Ho) TH = Ho;
       const uint32_t r_blk = (uint32_t)kt * 128;
       const uint32_t g_rows = (uint32_t)max((TH + a.halo) * P, kt + a.halo * P + a.halo);
       const uint32_t g_tile = (g_rows * 128 + 1023) & ~1023u;
       const uint32_t stage = 2 * r_blk + g_tiles * g_tile;
-      if (3 * stage + 1024 > kWgSmemBudget) continue;  // >= 3 stages: the kernel is fed from L2, latency must hide
+      if (3 * stage + kWgOnesBytes + 1024 > kWgSmemBudget) continue;  // >= 3 stages: fed from L2, latency must hide
       const long long tiles = (long long)((Wo + TW - 1) / TW) * ((Ho + TH - 1) / TH) * n_img;
-      // per tile: MMA time ~ taps-per-group * K steps * ~48 cycles (shared-memory-bound N = 64 MMA), load time ~ bytes
-      // moved L2 -> SMEM at ~32 B/cycle/SM; whichever is larger, plus a fixed per-tile cost
-      const double t_mma = (taps == 9 ? 4.5 : taps) * (kt / 16) * 48.0;
-      const double t_load = ((double)a.r_blocks * TH * TW * 128 + (double)g_tiles * (TH + a.halo) * P * 128) / 32.0;
-      const double cost = (double)tiles * ((t_mma > t_load ? t_mma : t_load) + 300.0);
+      // per tile and pass: MMA time ~ MMA groups * K steps * ~48 cycles (shared-memory-bound N = 64 MMA), load time ~
+      // bytes moved L2 -> SMEM at ~32 B/cycle/SM; whichever is larger, plus a fixed per-tile cost
+      const double t_mma = mma_groups * (kt / 16) * 48.0;
+      const double t_load = ((double)r_loads * TH * TW * 128 + (double)g_tiles * (TH + a.halo) * P * 128) / 32.0;
+      const double cost = (double)tiles * passes * ((t_mma > t_load ? t_mma : t_load) + 300.0);
       if (cost < best) {
         best = cost;
         found = true;
@@ -332,7 +418,7 @@ static bool wg_make_plan(int mode, int Ho, int Wo, int n_img, int m_total, int n
   if (!found) return false;
   a.tiles_x = (Wo + a.TW - 1) / a.TW;
   a.tiles_y = (Ho + a.TH - 1) / a.TH;
-  int stages = (int)((kWgSmemBudget - 1024) / a.stage_bytes);
+  int stages = (int)((kWgSmemBudget - 1024 - kWgOnesBytes) / a.stage_bytes);
   if (stages > kWgMaxStages) stages = kWgMaxStages;
   a.stages = stages;
   const long long tiles = (long long)a.tiles_x * a.tiles_y * n_img;
@@ -357,7 +443,8 @@ static bool wg_make_plan(int mode, int Ho, int Wo, int n_img, int m_total, int n
   while (splits > 1 && splits * per_split > (256LL << 20)) --splits;
   a.splits = (int)splits;
   pl->ws_bytes = (size_t)splits * per_split;
-  pl->smem_bytes = (uint32_t)a.stages * a.stage_bytes + 1024 + 256;
+  pl->ws_bias_bytes = a.bias ? (size_t)splits * a.m_pad * 4 : 0;
+  pl->smem_bytes = (uint32_t)a.stages * a.stage_bytes + kWgOnesBytes + 1024 + 256;
   const long long items = base_items * splits;
   pl->grid = (int)(items < wg_sms() ? items : wg_sms());
   return true;
@@ -371,23 +458,26 @@ static int wg_map(CUtensorMap* m, const b200_view& v, int bw, int bh) {
   return make_tmap_bf16(m, v.ptr, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-static int wg_launch(const WgMaps& maps, WgPlan& pl, float* dw, int c_src0, void* ws, size_t ws_bytes, cudaStream_t st) {
-  if (!ws || ws_bytes < pl.ws_bytes) return fail(-1, "wgrad (tcgen05): workspace too small (%zu < %zu)", ws_bytes, pl.ws_bytes);
+static int wg_launch(const WgMaps& maps, WgPlan& pl, float* dw, float* db, int c_src0, void* ws, size_t ws_bytes,
+                     cudaStream_t st) {
+  const size_t need = pl.ws_bytes + pl.ws_bias_bytes;
+  if (!ws || ws_bytes < need) return fail(-1, "wgrad (tcgen05): workspace too small (%zu < %zu)", ws_bytes, need);
   pl.a.ws = (float*)ws;
+  pl.a.ws_bias = (float*)((char*)ws + pl.ws_bytes);
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kWgSmemBudget + 2048);
+                                         (int)kWgSmemBudget + 4096);
     if (e != cudaSuccess) return fail((int)e, "wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_done = true;
   }
   wgrad_umma_kernel<<<pl.grid, kWgThreads, pl.smem_bytes, st>>>(maps, pl.a);
   int r = check_launch("wgrad_umma");
   if (r) return r;
-  const long long outs = (long long)pl.a.m_total * pl.a.n_total;
-  wgrad_umma_reduce_kernel<<<(unsigned)((outs + 255) / 256), 256, 0, st>>>(pl.a.ws, pl.a.splits, pl.a.taps, pl.a.m_total,
-                                                                           pl.a.n_total, pl.a.m_pad, pl.a.n_pad, c_src0,
-                                                                           pl.a.n_blks0, dw);
+  dim3 grid((unsigned)((pl.a.n_total + 31) / 32), (unsigned)pl.a.m_total);
+  wgrad_umma_reduce_kernel<<<grid, 32 * 9, 0, st>>>(pl.a.ws, pl.a.splits, pl.a.taps, pl.a.m_total, pl.a.n_total,
+                                                   pl.a.m_pad, pl.a.n_pad, c_src0, pl.a.n_blks0, dw,
+                                                   pl.a.bias ? pl.a.ws_bias : nullptr, pl.a.bias ? db : nullptr);
   return check_launch("wgrad_umma_reduce");
 }
 
@@ -397,6 +487,11 @@ static int conv_cin(const b200_conv_wgrad_params* p) {
   return c;
 }
 
+static bool conv_plan(const b200_conv_wgrad_params* p, WgPlan* pl) {
+  return wg_make_plan(0, p->dz.h, p->dz.w, p->dz.n, p->dz.c, conv_cin(p), p->src[0].c, p->taps, p->pad,
+                      p->db_f32 != nullptr, pl);
+}
+
 bool umma_conv_wgrad_ok(const b200_conv_wgrad_params* p) {
   if (!wg_device_ok()) return false;
   if (!wg_aligned(p->dz)) return false;
@@ -404,19 +499,18 @@ bool umma_conv_wgrad_ok(const b200_conv_wgrad_params* p) {
     if (!wg_aligned(p->src[i])) return false;
   if (p->num_src == 2 && p->src[0].c % 8 != 0) return false;
   WgPlan pl;
-  return wg_make_plan(0, p->dz.h, p->dz.w, p->dz.n, p->dz.c, conv_cin(p), p->src[0].c, p->taps, p->pad, &pl);
+  return conv_plan(p, &pl);
 }
 
 size_t umma_conv_wgrad_workspace(const b200_conv_wgrad_params* p) {
   WgPlan pl;
-  if (!wg_make_plan(0, p->dz.h, p->dz.w, p->dz.n, p->dz.c, conv_cin(p), p->src[0].c, p->taps, p->pad, &pl)) return 0;
-  return pl.ws_bytes + reduce_workspace_bytes(p->dz.c, 1);
+  if (!conv_plan(p, &pl)) return 0;
+  return pl.ws_bytes + pl.ws_bias_bytes;
 }
 
 int umma_conv_wgrad(const b200_conv_wgrad_params* p, void* ws, size_t ws_bytes, cudaStream_t st) {
   WgPlan pl;
-  if (!wg_make_plan(0, p->dz.h, p->dz.w, p->dz.n, p->dz.c, conv_cin(p), p->src[0].c, p->taps, p->pad, &pl))
-    return fail(-1, "conv_wgrad: no plan");
+  if (!conv_plan(p, &pl)) return fail(-1, "conv_wgrad: no plan");
   WgMaps maps;
   int r = wg_map(&maps.r, p->dz, pl.a.TW, 1);
   if (r) return fail(r, "conv_wgrad: tensor map for dz failed (%d)", r);
@@ -424,12 +518,7 @@ int umma_conv_wgrad(const b200_conv_wgrad_params* p, void* ws, size_t ws_bytes, 
     r = wg_map(&maps.g[i], p->src[i], pl.a.P, pl.a.TH + pl.a.halo);
     if (r) return fail(r, "conv_wgrad: tensor map for src[%d] failed (%d)", i, r);
   }
-  const size_t need = pl.ws_bytes + (p->db_f32 ? reduce_workspace_bytes(p->dz.c, 1) : 0);
-  if (ws_bytes < need) return fail(-1, "conv_wgrad (tcgen05): workspace too small (%zu < %zu)", ws_bytes, need);
-  r = wg_launch(maps, pl, p->dw_f32, p->src[0].c, ws, ws_bytes, st);
-  if (r) return r;
-  if (p->db_f32) return bias_grad(p->dz, p->db_f32, (char*)ws + pl.ws_bytes, st);
-  return 0;
+  return wg_launch(maps, pl, p->dw_f32, p->db_f32, p->src[0].c, ws, ws_bytes, st);
 }
 
 // ConvTranspose2d: row operand = x (M = cin), gathered operands = the four stride-2 sub-lattices of dy (N = cout)
@@ -447,18 +536,18 @@ bool umma_convt_wgrad_ok(const b200_convt_wgrad_params* p) {
   if (!wg_device_ok()) return false;
   if (!wg_aligned(p->x) || !wg_aligned(p->dy)) return false;
   WgPlan pl;
-  return wg_make_plan(1, p->x.h, p->x.w, p->x.n, p->x.c, p->dy.c, p->dy.c, 4, 0, &pl);
+  return wg_make_plan(1, p->x.h, p->x.w, p->x.n, p->x.c, p->dy.c, p->dy.c, 4, 0, false, &pl);
 }
 
 size_t umma_convt_wgrad_workspace(const b200_convt_wgrad_params* p) {
   WgPlan pl;
-  if (!wg_make_plan(1, p->x.h, p->x.w, p->x.n, p->x.c, p->dy.c, p->dy.c, 4, 0, &pl)) return 0;
+  if (!wg_make_plan(1, p->x.h, p->x.w, p->x.n, p->x.c, p->dy.c, p->dy.c, 4, 0, false, &pl)) return 0;
   return pl.ws_bytes + reduce_workspace_bytes(p->dy.c, 1);
 }
 
 int umma_convt_wgrad(const b200_convt_wgrad_params* p, void* ws, size_t ws_bytes, cudaStream_t st) {
   WgPlan pl;
-  if (!wg_make_plan(1, p->x.h, p->x.w, p->x.n, p->x.c, p->dy.c, p->dy.c, 4, 0, &pl))
+  if (!wg_make_plan(1, p->x.h, p->x.w, p->x.n, p->x.c, p->dy.c, p->dy.c, 4, 0, false, &pl))
     return fail(-1, "convt_wgrad: no plan");
   WgMaps maps;
   int r = wg_map(&maps.r, p->x, pl.a.TW, 1);
@@ -469,7 +558,7 @@ int umma_convt_wgrad(const b200_convt_wgrad_params* p, void* ws, size_t ws_bytes
   }
   const size_t need = pl.ws_bytes + (p->db_f32 ? reduce_workspace_bytes(p->dy.c, 1) : 0);
   if (ws_bytes < need) return fail(-1, "convt_wgrad (tcgen05): workspace too small (%zu < %zu)", ws_bytes, need);
-  r = wg_launch(maps, pl, p->dw_f32, p->dy.c, ws, ws_bytes, st);
+  r = wg_launch(maps, pl, p->dw_f32, nullptr, p->dy.c, ws, ws_bytes, st);
   if (r) return r;
   if (p->db_f32) return bias_grad(p->dy, p->db_f32, (char*)ws + pl.ws_bytes, st);
   return 0;
