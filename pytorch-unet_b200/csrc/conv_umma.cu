@@ -30,7 +30,8 @@ namespace b200 {
 constexpr int kUmmaThreads = 224;
 constexpr int kNA = 2;        // A (activation tile) stages
 constexpr int kMaxNB = 8;     // B (weight tile) stages
-constexpr uint32_t kSmemBudget = 200 * 1024;
+constexpr uint32_t kSmemBudget = 188 * 1024;   // A + B stages
+constexpr uint32_t kStageOutBytes = 4 * 8192;  // epilogue transpose buffers: 4 warps x [32 rows][64 cols] fp32
 
 struct TileMaps {
   CUtensorMap a[4];
@@ -84,7 +85,8 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = sA + kNA * a.a_stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (uint32_t)a.nb_stages * B_STAGE_BYTES);
+  uint8_t* sOut = sB + (uint32_t)a.nb_stages * B_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + kStageOutBytes);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kNA;
   uint64_t* b_full = a_empty + kNA;
@@ -173,6 +175,8 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     int astage = 0, bstage = 0;
     uint32_t aphase = 0, bphase = 0;
     int it = 0;
+    const int n_taps = a.taps, kx = a.kx, pitch = a.P, n_bstages = a.nb_stages;
+    const uint32_t a_stage_bytes = a.a_stage_bytes;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int buf = it % NBUF;
       mbar_wait(&t_empty[buf], ((it / NBUF) & 1) ^ 1);
@@ -182,12 +186,21 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       for (int s = 0; s < a.num_a; ++s) {
         for (int c0 = 0; c0 < a.a_c[s]; c0 += 64) {
           mbar_wait(&a_full[astage], aphase);
-          const uint32_t a_base = smem_u32(sA + astage * a.a_stage_bytes);
-          for (int tap = 0; tap < a.taps; ++tap) {
+          const uint32_t a_base = smem_u32(sA + astage * a_stage_bytes);
+          int tap_s = -1;
+          uint32_t tap_row_off = 0;
+          const uint64_t a_desc0 = umma_desc(desc_hi, a_base);
+          for (int tap = 0; tap < n_taps; ++tap) {
             mbar_wait(&b_full[bstage], bphase);
             tc_fence_after_sync();
-            const int r = tap / a.kx, sx = tap - r * a.kx;
-            const uint64_t a_desc = umma_desc(desc_hi, a_base + (uint32_t)(r * a.P + sx) * 128);
+            // tap (r, s) reads the A tile r*P + s rows further: 128 B per row = 8 descriptor units
+            if (++tap_s == kx) {
+              tap_s = 0;
+              tap_row_off += (uint32_t)(pitch - kx + 1) * 8;
+            } else if (tap != 0) {
+              tap_row_off += 8;
+            }
+            const uint64_t a_desc = a_desc0 + tap_row_off;
             const uint64_t b_desc = umma_desc(desc_hi, smem_u32(sB + bstage * B_STAGE_BYTES));
             if (elect_one()) {
 #pragma unroll
@@ -203,7 +216,7 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
             }
             __syncwarp();
             accum = 1;
-            if (++bstage == a.nb_stages) {
+            if (++bstage == n_bstages) {
               bstage = 0;
               bphase ^= 1;
             }
@@ -220,8 +233,19 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       __syncwarp();
     }
   } else {
-    // ================= epilogue: 4 warps, warp w owns TMEM lanes 32*(w%4) .. +31
+    // ================= epilogue: 4 warps, warp w owns TMEM lanes 32*(w%4) .. +31 (= 32 output positions).
+    // tcgen05.ld gives every lane one position's row of accumulators, but a row-per-lane store touches 32 different
+    // 128-byte lines per instruction (measured: the old epilogue, not the MMAs, bounded the 64/128-channel layers).
+    // So each warp transposes through its own 8 KiB shared-memory buffer ([32 rows][CP cols] fp32, 16-byte chunks
+    // XOR-swizzled by row): after the transpose CP/8 consecutive lanes own one position's contiguous CP*2 bytes, and
+    // bias / ReLU / mask / bf16 conversion happen on that side, so mask loads and output stores are full lines.
+    constexpr int CP = BN < 64 ? BN : 64;   // columns per pass
+    constexpr int LPR = CP / 8;             // lanes per row on the store side (one 16-byte bf16 chunk each)
+    constexpr int RPI = 32 / LPR;           // rows per store iteration
+    constexpr int CH16 = CP / 4;            // 16-byte fp32 chunks per staged row
     const int quarter = warp & 3;
+    float* stg = reinterpret_cast<float*>(sOut + quarter * 8192);
+    const int rsub = lane / LPR, cch = lane % LPR;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const TileCoord t = decode_tile(a, tile, BN);
@@ -238,41 +262,73 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
         const int ty = q / a.P, tx = q - ty * a.P;
         const int oy = t.y0 + ty, ox = t.x0 + tx;
         const bool valid = ty < a.TH && tx < a.TW && oy < a.Ho && ox < a.Wo;
-        const long long off = valid ? dst.off(t.n, oy, ox) + ch0 : 0;
+        const long long off = valid ? dst.off(t.n, oy, ox) + ch0 : -1;  // -1 = nothing to store for this position
         const uint32_t taddr = tmem_base + buf * (MB * BN) + mb * BN + (uint32_t(quarter * 32) << 16);
 #pragma unroll 1
-        for (int col0 = 0; col0 < BN; col0 += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr + col0, v);
-          tmem_ld_wait();
-          if (valid) {
-#pragma unroll
-            for (int g8 = 0; g8 < 4; ++g8) {
-              const int col = col0 + g8 * 8;
-              if (t.n0 + col < a.cout_total) {
-                float f[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g8 * 8 + j]);
-                if (a.bias) {
-                  const float4 b0 = *reinterpret_cast<const float4*>(a.bias + ch0 + col);
-                  const float4 b1 = *reinterpret_cast<const float4*>(a.bias + ch0 + col + 4);
-                  f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                  f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-                }
-                if (a.relu) {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
-                }
-                if (mk) {
-                  float m[8];
-                  unpack8(*reinterpret_cast<const bf16x8*>(mk + off + col), m);
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) f[j] = m[j] > 0.f ? f[j] : 0.f;
-                }
-                *reinterpret_cast<bf16x8*>(dst.p + off + col) = pack8(f);
-              }
+        for (int col0 = 0; col0 < BN; col0 += CP) {
+          uint32_t v[CP];
+          {
+            uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+            tmem_ld_32x32(taddr + col0, v0);
+            if (CP == 64) {
+              uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[CP - 32]);
+              tmem_ld_32x32(taddr + col0 + 32, v1);
             }
           }
+          tmem_ld_wait();
+          // row-owner side: lane writes its position's CP accumulators (16-byte chunk j goes to slot j ^ (lane & 15))
+#pragma unroll
+          for (int j = 0; j < CH16; ++j) {
+            const int slot = (j ^ (lane & (CH16 - 1)));
+            *reinterpret_cast<uint4*>(stg + lane * CP + slot * 4) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          __syncwarp();
+          // store side: this lane's 8 columns are fixed for the pass
+          const int col = col0 + cch * 8;
+          const bool col_ok = t.n0 + col < a.cout_total;
+          float bv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bv[j] = 0.f;
+          if (a.bias && col_ok) {
+            const float4 b0 = *reinterpret_cast<const float4*>(a.bias + ch0 + col);
+            const float4 b1 = *reinterpret_cast<const float4*>(a.bias + ch0 + col + 4);
+            bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w;
+            bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+          }
+          // phase A: all row offsets and (dgrad) all mask vectors of the pass first, so the global loads overlap
+          long long offs[LPR];
+          bf16x8 mv[LPR];
+#pragma unroll
+          for (int i = 0; i < LPR; ++i) {
+            offs[i] = __shfl_sync(0xffffffffu, off, i * RPI + rsub);
+            if (!col_ok) offs[i] = -1;
+            mv[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+            if (mk && offs[i] >= 0) mv[i] = *reinterpret_cast<const bf16x8*>(mk + offs[i] + col);
+          }
+          // phase B: bias / ReLU / mask / convert / store, one contiguous 16-byte chunk per lane and row
+#pragma unroll
+          for (int i = 0; i < LPR; ++i) {
+            const int R = i * RPI + rsub;
+            if (offs[i] >= 0) {
+              const int s0 = ((2 * cch) ^ (R & (CH16 - 1))), s1 = ((2 * cch + 1) ^ (R & (CH16 - 1)));
+              const float4 f0 = *reinterpret_cast<const float4*>(stg + R * CP + s0 * 4);
+              const float4 f1 = *reinterpret_cast<const float4*>(stg + R * CP + s1 * 4);
+              float f[8] = {f0.x + bv[0], f0.y + bv[1], f0.z + bv[2], f0.w + bv[3],
+                            f1.x + bv[4], f1.y + bv[5], f1.z + bv[6], f1.w + bv[7]};
+              if (a.relu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+              }
+              if (mk) {
+                float m[8];
+                unpack8(mv[i], m);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = m[j] > 0.f ? f[j] : 0.f;
+              }
+              *reinterpret_cast<bf16x8*>(dst.p + offs[i] + col) = pack8(f);
+            }
+          }
+          __syncwarp();
         }
       }
       tc_fence_before_sync();
@@ -305,6 +361,8 @@ static bool device_is_sm100() {
 }
 
 static int pick_bn(int cout_total, int ndst, int dst_c0) {
+  // (BN = 256 needs all 512 TMEM columns for one MB = 2 tile, so its epilogue is not overlapped — the profile shows the MMA
+  // warp waiting ~27 % of the time on it — yet BN = 128 measured slower on the deep layers: A is streamed twice.)
   const int cands[4] = {256, 128, 64, 32};
   for (int i = 0; i < 4; ++i) {
     const int bn = cands[i];
@@ -355,7 +413,7 @@ static bool make_plan(int Ho, int Wo, int n_img, int halo, int cout_total, int n
   if (nb > kMaxNB) nb = kMaxNB;
   if (nb < 2) return false;
   pl->nb_stages = nb;
-  pl->smem_bytes = kNA * pl->a_stage_bytes + nb * bn * 128 + 1024 /*align*/ + 512 /*barriers*/;
+  pl->smem_bytes = kNA * pl->a_stage_bytes + nb * bn * 128 + kStageOutBytes + 1024 /*align*/ + 512 /*barriers*/;
   return true;
 }
 
@@ -379,7 +437,8 @@ static int launch_inst(const TileMaps& maps, const UmmaArgs& a, const Plan& pl, 
   auto kern = umma_conv_kernel<MB, BN>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget + 2048);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(kSmemBudget + kStageOutBytes + 2048));
     if (e != cudaSuccess) return fail((int)e, "umma_conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_done = true;
   }

@@ -187,38 +187,52 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
     uint32_t phase = 0;
     int it = 0;
     const int ksteps = a.kt_rows / 16;
+    const uint32_t stage_bytes = a.stage_bytes, r_blk_bytes = a.r_blk_bytes;
+    const int n_stages = a.stages;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x)
       for (int grp = 0; grp < a.tap_groups; ++grp, ++it) {
         const WgItem w = decode_item(a, item, grp);
         const bool do_bias = a.bias && w.nb == 0 && grp == 0;
+        // per-item table of gathered-operand start offsets (in descriptor units of 16 B): no division / constant
+        // loads inside the issue loop — with N = 64 MMAs (48 cycles each) the issuing lane is otherwise the bottleneck
+        uint32_t goff[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          uint32_t o = 0;
+          if (j < w.ntap) {
+            if (a.paired) {
+              o = (uint32_t)((j >> 1) * a.P + (j & 1) * 2) * 8;  // sigma = r*P + {0, 2}; 128 B = 8 units
+            } else if (a.mode == 0) {
+              const int tap = w.tap0 + j;
+              const int r = tap / a.kx, sx = tap - r * a.kx;
+              o = (uint32_t)(r * a.P + sx) * 8;
+            } else {
+              o = (uint32_t)(w.tap0 + j) * (a.g_tile_bytes >> 4);
+            }
+          }
+          goff[j] = o;
+        }
+        const int ntap = w.ntap;
         mbar_wait(t_empty, (it & 1) ^ 1);
         tc_fence_after_sync();
         uint32_t accum = 0;
         for (int tile = w.tile0; tile < w.tile1; ++tile) {
           mbar_wait(&full[stage], phase);
           tc_fence_after_sync();
-          const uint32_t r_base = smem_u32(smem + stage * a.stage_bytes);
-          const uint32_t g_base = r_base + 2 * a.r_blk_bytes;
+          const uint32_t r_base = smem_u32(smem + stage * stage_bytes);
           const uint64_t r_desc = umma_desc(hi_r, r_base);
+          const uint64_t g_desc0 = umma_desc(hi_g, r_base + 2 * r_blk_bytes);
           if (elect_one()) {
-            for (int j = 0; j < w.ntap; ++j) {
-              uint32_t g_tap;
-              if (a.paired) {
-                const int r = j >> 1, sx = (j & 1) * 2;  // sigma = r*P + {0, 2}
-                g_tap = g_base + (uint32_t)(r * a.P + sx) * 128;
-              } else if (a.mode == 0) {
-                const int tap = w.tap0 + j;
-                const int r = tap / a.kx, sx = tap - r * a.kx;
-                g_tap = g_base + (uint32_t)(r * a.P + sx) * 128;
-              } else {
-                g_tap = g_base + (w.tap0 + j) * a.g_tile_bytes;
-              }
-              const uint64_t g_desc = umma_desc(hi_g, g_tap);
-              const uint32_t d = tmem_base + j * 64;
-              // one K step = 16 pixel rows = 2048 B = 128 in the descriptor's (address >> 4) field
-              umma_bf16(d, r_desc, g_desc, idesc, accum);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+              if (j < ntap) {
+                const uint64_t g_desc = g_desc0 + goff[j];
+                const uint32_t d = tmem_base + j * 64;
+                // one K step = 16 pixel rows = 2048 B = 128 in the descriptor's (address >> 4) field
+                umma_bf16(d, r_desc, g_desc, idesc, accum);
 #pragma unroll 4
-              for (int k = 1; k < ksteps; ++k) umma_bf16(d, r_desc + (uint64_t)k * 128, g_desc + (uint64_t)k * 128, idesc, 1u);
+                for (int k = 1; k < ksteps; ++k) umma_bf16(d, r_desc + (uint64_t)k * 128, g_desc + (uint64_t)k * 128, idesc, 1u);
+              }
             }
             if (do_bias) {
               umma_bf16(tmem_base + kWgBiasCol, r_desc, ones_desc, idesc_bias, accum);
@@ -230,7 +244,7 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
           }
           __syncwarp();
           accum = 1;
-          if (++stage == a.stages) {
+          if (++stage == n_stages) {
             stage = 0;
             phase ^= 1;
           }
