@@ -95,11 +95,13 @@ smallc_fwd_kernel(DView src, DView dst, const float* __restrict__ w, const float
   }
 }
 
-// partial layout per block: [64 couts][9*CIN] weights followed by [64] bias sums
+// partial layout per block: [64 couts][9*CIN] weights followed by [64] bias sums.
+// Thread = CPT output channels x all 9*CIN taps; one loop iteration = a strip of 4 consecutive pixels of one row, whose
+// 3 x 6 input window is loaded once per input channel (sliding window) and whose index arithmetic is paid once.
 template <int CIN, int CPT>
 __global__ void __launch_bounds__(kScThreads)
 smallc_wgrad_kernel(DView dz, DView src, int pad, float* __restrict__ partial) {
-  constexpr int LPP = 64 / CPT;       // lanes per pixel
+  constexpr int LPP = 64 / CPT;       // lanes per pixel strip
   constexpr int NT = 9 * CIN;         // taps x input channels
   constexpr int ROW = 64 * NT + 64;   // floats per block partial
   extern __shared__ float red[];      // [8 warps][ROW]
@@ -117,50 +119,68 @@ smallc_wgrad_kernel(DView dz, DView src, int pad, float* __restrict__ partial) {
 #pragma unroll
     for (int j = 0; j < NT; ++j) acc[i][j] = 0.f;
   }
-  const long long hw = (long long)dz.h * dz.w;
-  const long long npix = hw * dz.n;
+  const int groups_per_row = (dz.w + 3) >> 2;
+  const unsigned total_groups = (unsigned)dz.n * dz.h * groups_per_row;
   if (o0 < cout) {
-    for (long long p = (long long)blockIdx.x * slots + slot; p < npix; p += (long long)gridDim.x * slots) {
-      const int n = (int)(p / hw);
-      const long long r2 = p - n * hw;
-      const int oy = (int)(r2 / dz.w), ox = (int)(r2 - (long long)oy * dz.w);
-      float z[CPT];
-      const bf16* zp = dz.p + dz.off(n, oy, ox) + o0;
-      if (CPT == 16) {
-        float t[8];
-        unpack8(*reinterpret_cast<const bf16x8*>(zp), t);
+    for (unsigned g = blockIdx.x * slots + slot; g < total_groups; g += gridDim.x * slots) {
+      const unsigned xg = g % groups_per_row;
+      const unsigned t2 = g / groups_per_row;
+      const int oy = (int)(t2 % dz.h), n = (int)(t2 / dz.h);
+      const int ox0 = (int)xg * 4;
+      float z[4][CPT];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) z[i] = t[i];
-        unpack8(*reinterpret_cast<const bf16x8*>(zp + 8), t);
+      for (int p = 0; p < 4; ++p) {
+        if (ox0 + p < dz.w) {
+          const bf16* zp = dz.p + dz.off(n, oy, ox0 + p) + o0;
+          if (CPT == 16) {
+            float t[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(zp), t);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) z[(8 + i) % CPT] = t[i];
-      } else if (CPT == 8) {
-        float t[8];
-        unpack8(*reinterpret_cast<const bf16x8*>(zp), t);
+            for (int i = 0; i < 8; ++i) z[p][i] = t[i];
+            unpack8(*reinterpret_cast<const bf16x8*>(zp + 8), t);
 #pragma unroll
-        for (int i = 0; i < CPT; ++i) z[i] = t[i % 8];
-      } else {
-        const uint2 u = *reinterpret_cast<const uint2*>(zp);
-        const float2 a = bf2x_to_f2(u.x), b = bf2x_to_f2(u.y);
-        z[0] = a.x;
-        z[1 % CPT] = a.y;
-        z[2 % CPT] = b.x;
-        z[3 % CPT] = b.y;
+            for (int i = 0; i < 8; ++i) z[p][(8 + i) % CPT] = t[i];
+          } else if (CPT == 8) {
+            float t[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(zp), t);
+#pragma unroll
+            for (int i = 0; i < CPT; ++i) z[p][i] = t[i % 8];
+          } else {
+            const uint2 u = *reinterpret_cast<const uint2*>(zp);
+            const float2 a2 = bf2x_to_f2(u.x), b2 = bf2x_to_f2(u.y);
+            z[p][0] = a2.x;
+            z[p][1 % CPT] = a2.y;
+            z[p][2 % CPT] = b2.x;
+            z[p][3 % CPT] = b2.y;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < CPT; ++i) z[p][i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) accb[i] += z[p][i];
       }
-      float xv[NT];
 #pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int iy = oy + t / 3 - pad, ix = ox + t % 3 - pad;
-        const bool ok = iy >= 0 && iy < src.h && ix >= 0 && ix < src.w;
-        const bf16* xp = src.p + (ok ? src.off(n, iy, ix) : 0);
+      for (int c = 0; c < CIN; ++c) {
+        float xin[3][6];
 #pragma unroll
-        for (int c = 0; c < CIN; ++c) xv[c * 9 + t] = ok ? bf2f(xp[c]) : 0.f;
-      }
+        for (int r = 0; r < 3; ++r) {
+          const int iy = oy + r - pad;
+          const bool yok = iy >= 0 && iy < src.h;
 #pragma unroll
-      for (int i = 0; i < CPT; ++i) {
-        accb[i] += z[i];
+          for (int j = 0; j < 6; ++j) {
+            const int ix = ox0 + j - pad;
+            xin[r][j] = (yok && ix >= 0 && ix < src.w) ? bf2f(src.p[src.off(n, iy, ix) + c]) : 0.f;
+          }
+        }
 #pragma unroll
-        for (int j = 0; j < NT; ++j) acc[i][j] += z[i] * xv[j];
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int sx = 0; sx < 3; ++sx)
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+              for (int i = 0; i < CPT; ++i) acc[i][c * 9 + r * 3 + sx] += z[p][i] * xin[r][p + sx];
       }
     }
   }

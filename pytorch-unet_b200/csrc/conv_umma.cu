@@ -21,6 +21,8 @@
 // single-thread tcgen05.mma issuer, 3..6 = epilogue (tcgen05.ld -> bias / ReLU / mask -> bf16 -> global).
 // Accumulators: MB x BN fp32 columns in TMEM, double-buffered when 2*MB*BN <= 512 so the epilogue of tile i overlaps
 // the MMAs of tile i+1.
+#include <cstdlib>
+
 #include "conv_impl.h"
 #include "ptx.cuh"
 #include "tmap.h"
@@ -59,10 +61,15 @@ struct TileCoord {
   int n, y0, x0, n0;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const UmmaArgs& a, int tile, int bn) {
+// CL = 1: work item = tile, N tile fastest.  CL = 2 (CTA pair sharing the weight tiles by TMA multicast): work item =
+// pair of neighbouring pixel tiles with the SAME N tile; CTA `rank` of the cluster takes pixel tile 2*pair + rank (an
+// odd tail is duplicated: both CTAs then compute and store the same tile, which is harmless).
+template <int CL>
+__device__ __forceinline__ TileCoord decode_tile(const UmmaArgs& a, int work, int rank, int bn) {
   TileCoord t;
-  const int nt = tile % a.n_ntiles;
-  int pt = tile / a.n_ntiles;
+  const int nt = work % a.n_ntiles;
+  int pt = work / a.n_ntiles;
+  if (CL == 2) pt = min(2 * pt + rank, a.tiles_x * a.tiles_y * a.n_img - 1);
   const int txi = pt % a.tiles_x;
   pt /= a.tiles_x;
   const int tyi = pt % a.tiles_y;
@@ -73,7 +80,7 @@ __device__ __forceinline__ TileCoord decode_tile(const UmmaArgs& a, int tile, in
   return t;
 }
 
-template <int MB, int BN>
+template <int MB, int BN, int CL>
 __global__ void __launch_bounds__(kUmmaThreads, 1)
 umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ UmmaArgs a) {
   constexpr int NBUF = (2 * MB * BN <= 512) ? 2 : 1;
@@ -97,7 +104,12 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = a.tiles_x * a.tiles_y * a.n_img * a.n_ntiles;
+  // work iteration space (see decode_tile)
+  const int rank = CL == 2 ? (int)cluster_ctarank() : 0;
+  const int pix_tiles = a.tiles_x * a.tiles_y * a.n_img;
+  const int total_tiles = (CL == 2 ? (pix_tiles + 1) / 2 : pix_tiles) * a.n_ntiles;
+  const int work0 = CL == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int work_step = CL == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kNA; ++i) {
@@ -106,7 +118,7 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     }
     for (int i = 0; i < kMaxNB; ++i) {
       mbar_init(&b_full[i], 1);
-      mbar_init(&b_empty[i], 1);
+      mbar_init(&b_empty[i], CL);  // a weight stage is rewritten (in both CTAs) only when both CTAs have consumed it
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&t_full[i], 1);
@@ -121,6 +133,7 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before_sync();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();  // the peer's barriers must be initialised before anything is multicast to them
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -129,8 +142,8 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(a, tile, BN);
+      for (int tile = work0; tile < total_tiles; tile += work_step) {
+        const TileCoord t = decode_tile<CL>(a, tile, rank, BN);
         for (int s = 0; s < a.num_a; ++s) {
           for (int c0 = 0; c0 < a.a_c[s]; c0 += 64) {
             mbar_wait(&a_empty[stage], phase ^ 1);
@@ -149,13 +162,19 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(a, tile, BN);
+      for (int tile = work0; tile < total_tiles; tile += work_step) {
+        const TileCoord t = decode_tile<CL>(a, tile, rank, BN);
         for (int s = 0; s < a.num_a; ++s) {
           for (int c0 = 0; c0 < a.a_c[s]; c0 += 64) {
             for (int tap = 0; tap < a.taps; ++tap) {
               mbar_wait(&b_empty[stage], phase ^ 1);
               mbar_arrive_expect_tx(&b_full[stage], B_STAGE_BYTES);
+              if (CL == 2) {
+                // this CTA fetches rows [rank*BN/2, +BN/2) of the weight tile and multicasts them into both CTAs; the
+                // other half arrives from the peer.  L2 -> SMEM weight traffic per CTA is halved.
+                tma_load_2d_multicast(&maps.b, &b_full[stage], sB + stage * B_STAGE_BYTES + rank * (B_STAGE_BYTES / 2),
+                                      tap * a.kpad + a.a_koff[s] + c0, t.n0 + rank * (BN / 2), (uint16_t)0x3);
+              } else
               tma_load_2d(&maps.b, &b_full[stage], sB + stage * B_STAGE_BYTES, tap * a.kpad + a.a_koff[s] + c0, t.n0);
               if (++stage == a.nb_stages) {
                 stage = 0;
@@ -177,7 +196,7 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     int it = 0;
     const int n_taps = a.taps, kx = a.kx, pitch = a.P, n_bstages = a.nb_stages;
     const uint32_t a_stage_bytes = a.a_stage_bytes;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = work0; tile < total_tiles; tile += work_step, ++it) {
       const int buf = it % NBUF;
       mbar_wait(&t_empty[buf], ((it / NBUF) & 1) ^ 1);
       tc_fence_after_sync();
@@ -212,7 +231,10 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
                 for (int kk = 1; kk < 4; ++kk)
                   umma_bf16(acc + mb * BN, a_desc + (uint64_t)(mb * 1024 + kk * 2), b_desc + (uint64_t)(kk * 2), idesc, 1u);
               }
-              umma_commit(&b_empty[bstage]);
+              if (CL == 2)
+                umma_commit_multicast(&b_empty[bstage], (uint16_t)0x3);
+              else
+                umma_commit(&b_empty[bstage]);
             }
             __syncwarp();
             accum = 1;
@@ -247,8 +269,8 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     float* stg = reinterpret_cast<float*>(sOut + quarter * 8192);
     const int rsub = lane / LPR, cch = lane % LPR;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const TileCoord t = decode_tile(a, tile, BN);
+    for (int tile = work0; tile < total_tiles; tile += work_step, ++it) {
+      const TileCoord t = decode_tile<CL>(a, tile, rank, BN);
       const int buf = it % NBUF;
       mbar_wait(&t_full[buf], (it / NBUF) & 1);
       tc_fence_after_sync();
@@ -338,12 +360,17 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
   }
   tc_fence_before_sync();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();  // the peer may still multicast into this CTA's shared memory / barriers
   if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
 // ------------------------------------------------------------------ host side
+// 0 disables the CTA-pair (multicast) variant; B200UNET_NO_CLUSTER=1 in the environment sets it (for A/B timing)
+static int g_umma_cluster = getenv("B200UNET_NO_CLUSTER") ? 0 : 1;
+static int g_umma_max_mb = getenv("B200UNET_MAX_MB") ? atoi(getenv("B200UNET_MAX_MB")) : 4;
+
 struct Plan {
-  int MB, BN, P, TH, TW, halo;
+  int MB, BN, CL, P, TH, TW, halo;
   int tiles_x, tiles_y, n_ntiles;
   uint32_t a_stage_bytes, a_tx_bytes, smem_bytes;
   int nb_stages;
@@ -378,8 +405,9 @@ static bool make_plan(int Ho, int Wo, int n_img, int halo, int cout_total, int n
   pl->halo = halo;
   double best = 1e30;
   bool found = false;
-  for (int mb = 1; mb <= 2; ++mb) {
+  for (int mb = 1; mb <= g_umma_max_mb; mb *= 2) {
     if (mb * bn > 512) continue;
+    if (mb == 4 && bn > 64) continue;  // MB = 4 only where TMEM stays double-buffered
     for (int P = halo + 1; P <= 256 && P <= Wo + halo + 8; ++P) {
       const int TW = P - halo;
       int TH = (mb * 128) / P;
@@ -391,7 +419,7 @@ static bool make_plan(int Ho, int Wo, int n_img, int halo, int cout_total, int n
       if (kNA * a_stage + 2 * (uint32_t)bn * 128 + 1024 > kSmemBudget) continue;
       const long long tiles = (long long)((Wo + TW - 1) / TW) * ((Ho + TH - 1) / TH) * n_img;
       // cost: MMA rows issued, + fixed per-tile overhead, + mild preference for MB = 2 (halves weight traffic)
-      double cost = (double)tiles * (mb * 128 + 24) * (mb == 1 ? 1.06 : 1.0);
+      double cost = (double)tiles * (mb * 128 + 24) * (mb == 1 ? 1.06 : (mb == 4 ? 0.94 : 1.0));
       if (cost < best) {
         best = cost;
         found = true;
@@ -405,6 +433,8 @@ static bool make_plan(int Ho, int Wo, int n_img, int halo, int cout_total, int n
   }
   if (!found) return false;
   pl->BN = bn;
+  // CTA pairs share the weight tiles (TMA multicast): worth it once there are enough pixel tiles for every pair
+  pl->CL = (g_umma_cluster && bn >= 32 && (long long)((Wo + pl->TW - 1) / pl->TW) * ((Ho + pl->TH - 1) / pl->TH) * n_img >= 4) ? 2 : 1;
   pl->tiles_x = (Wo + pl->TW - 1) / pl->TW;
   pl->tiles_y = (Ho + pl->TH - 1) / pl->TH;
   pl->n_ntiles = (cout_total + bn - 1) / bn;
@@ -432,9 +462,9 @@ static int make_b_map(CUtensorMap* m, const void* w, int rows, int cols, int bn)
   return make_tmap_bf16(m, w, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int MB, int BN>
+template <int MB, int BN, int CL>
 static int launch_inst(const TileMaps& maps, const UmmaArgs& a, const Plan& pl, cudaStream_t st) {
-  auto kern = umma_conv_kernel<MB, BN>;
+  auto kern = umma_conv_kernel<MB, BN, CL>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -442,11 +472,31 @@ static int launch_inst(const TileMaps& maps, const UmmaArgs& a, const Plan& pl, 
     if (e != cudaSuccess) return fail((int)e, "umma_conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_done = true;
   }
-  const int total = a.tiles_x * a.tiles_y * a.n_img * a.n_ntiles;
   static int sms = 0;
   if (!sms) sms = b200unet_num_sms();
-  const int grid = total < sms ? total : sms;
-  kern<<<grid, kUmmaThreads, pl.smem_bytes, st>>>(maps, a);
+  const int pix = a.tiles_x * a.tiles_y * a.n_img;
+  if (CL == 2) {
+    const int pairs = (pix + 1) / 2 * a.n_ntiles;
+    int clusters = pairs < sms / 2 ? pairs : sms / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kUmmaThreads);
+    cfg.dynamicSmemBytes = pl.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps, a);
+    if (e != cudaSuccess) return fail((int)e, "umma_conv: cluster launch: %s", cudaGetErrorString(e));
+  } else {
+    const int total = pix * a.n_ntiles;
+    const int grid = total < sms ? total : sms;
+    kern<<<grid, kUmmaThreads, pl.smem_bytes, st>>>(maps, a);
+  }
   return check_launch("umma_conv");
 }
 
@@ -460,8 +510,9 @@ static int launch_plan(const TileMaps& maps, UmmaArgs& a, const Plan& pl, cudaSt
   a.a_stage_bytes = pl.a_stage_bytes;
   a.a_tx_bytes = pl.a_tx_bytes;
   a.nb_stages = pl.nb_stages;
-#define B200_INST(MBv, BNv) \
-  if (pl.MB == MBv && pl.BN == BNv) return launch_inst<MBv, BNv>(maps, a, pl, st);
+#define B200_INST(MBv, BNv)                                                                   \
+  if (pl.MB == MBv && pl.BN == BNv)                                                           \
+    return pl.CL == 2 ? launch_inst<MBv, BNv, 2>(maps, a, pl, st) : launch_inst<MBv, BNv, 1>(maps, a, pl, st);
   B200_INST(1, 32)
   B200_INST(1, 64)
   B200_INST(1, 128)
@@ -470,6 +521,8 @@ static int launch_plan(const TileMaps& maps, UmmaArgs& a, const Plan& pl, cudaSt
   B200_INST(2, 64)
   B200_INST(2, 128)
   B200_INST(2, 256)
+  B200_INST(4, 32)
+  B200_INST(4, 64)
 #undef B200_INST
   return fail(-1, "umma_conv: no kernel instance for MB=%d BN=%d", pl.MB, pl.BN);
 }
@@ -502,7 +555,7 @@ int umma_conv_fwd(const b200_conv_fwd_params* p, cudaStream_t st) {
     koff += (p->src[i].c + 63) / 64 * 64;
   }
   a.kpad = koff;
-  int r = make_b_map(&maps.b, p->w_packed, p->dst.c, p->taps * a.kpad, pl.BN);
+  int r = make_b_map(&maps.b, p->w_packed, p->dst.c, p->taps * a.kpad, pl.BN / pl.CL);
   if (r) return fail(r, "conv_fwd: weight tensor map failed (%d)", r);
   a.taps = p->taps;
   a.kx = p->taps == 9 ? 3 : 1;
@@ -553,7 +606,7 @@ int umma_conv_dgrad(const b200_conv_dgrad_params* p, cudaStream_t st) {
   a.a_c[0] = p->dz.c;
   a.a_koff[0] = 0;
   a.kpad = (p->dz.c + 63) / 64 * 64;
-  r = make_b_map(&maps.b, p->w_packed, cin, p->taps * a.kpad, pl.BN);
+  r = make_b_map(&maps.b, p->w_packed, cin, p->taps * a.kpad, pl.BN / pl.CL);
   if (r) return fail(r, "conv_dgrad: weight tensor map failed (%d)", r);
   a.taps = p->taps;
   a.kx = p->taps == 9 ? 3 : 1;
@@ -601,7 +654,7 @@ int umma_convt_fwd(const b200_convt_fwd_params* p, cudaStream_t st) {
   if (r) return fail(r, "convt_fwd: tensor map for x failed (%d)", r);
   a.a_c[0] = p->x.c;
   a.kpad = (p->x.c + 63) / 64 * 64;
-  r = make_b_map(&maps.b, p->w_packed, 4 * p->y.c, a.kpad, pl.BN);
+  r = make_b_map(&maps.b, p->w_packed, 4 * p->y.c, a.kpad, pl.BN / pl.CL);
   if (r) return fail(r, "convt_fwd: weight tensor map failed (%d)", r);
   a.taps = 1;
   a.kx = 1;
@@ -640,7 +693,7 @@ int umma_convt_dgrad(const b200_convt_dgrad_params* p, cudaStream_t st) {
     a.a_koff[ab] = ab * opad;
   }
   a.kpad = 4 * opad;
-  int r = make_b_map(&maps.b, p->w_packed, p->dx.c, 4 * opad, pl.BN);
+  int r = make_b_map(&maps.b, p->w_packed, p->dx.c, 4 * opad, pl.BN / pl.CL);
   if (r) return fail(r, "convt_dgrad: weight tensor map failed (%d)", r);
   a.taps = 1;
   a.kx = 1;

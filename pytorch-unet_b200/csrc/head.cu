@@ -10,7 +10,7 @@
 namespace b200 {
 
 constexpr int kHeadThreads = 256;
-constexpr int kHeadMaxBlocks = 2 * kNumSMsB200;
+constexpr int kHeadMaxBlocks = 8 * kNumSMsB200;  // HBM-bound, one 16-byte load in flight per thread: needs many resident warps
 constexpr long long kIgnoreIndex = -100;
 
 enum { HEAD_FWD = 0, HEAD_CE_FWD = 1, HEAD_BWD = 2, HEAD_CE_BWD = 3 };
