@@ -20,6 +20,8 @@
 // Work item = (pixel split, 64-channel N block, 128-channel M block); fp32 partials [split][tap][M][N] (+ [split][M]
 // for the bias); a second kernel reduces the splits in a fixed order and writes the state_dict layout, so results are
 // run-to-run reproducible.
+#include <cstdlib>
+
 #include "chan_reduce.cuh"
 #include "conv_impl.h"
 #include "ptx.cuh"
@@ -44,7 +46,8 @@ struct WgArgs {
   int bias;    // accumulate column sums of the row operand (conv bias gradient)
   int m_total, n_total;
   int g_c[2];   // conv: channels per concat source
-  int n_blks0;  // conv: number of 64-blocks of source 0
+  int n_blks0;  // conv: number of N blocks of source 0
+  int nbw;      // N block width: 64, or 128 (two 64-channel sub-tiles, one N = 128 MMA at the full tensor rate)
   int taps, kx, halo, pad;
   int P, TH, TW, kt_rows;
   int tiles_x, tiles_y, n_img;
@@ -138,10 +141,10 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
         for (int grp = 0; grp < a.tap_groups; ++grp) {
           const WgItem w = decode_item(a, item, grp);
           // gathered-operand source of this N block
-          int gsrc = 0, gc0 = w.nb * 64;
+          int gsrc = 0, gc0 = w.nb * a.nbw;
           if (a.mode == 0 && w.nb >= a.n_blks0) {
             gsrc = 1;
-            gc0 = (w.nb - a.n_blks0) * 64;
+            gc0 = (w.nb - a.n_blks0) * a.nbw;
           }
           for (int tile = w.tile0; tile < w.tile1; ++tile) {
             const int txi = tile % a.tiles_x;
@@ -150,7 +153,7 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
             const int y0 = tyi * a.TH, x0 = txi * a.TW;
             uint8_t* st = smem + stage * a.stage_bytes;
             mbar_wait(&empty[stage], phase ^ 1);
-            const uint32_t tx_bytes = (uint32_t)r_loads * a.TH * a.TW * 128 + (uint32_t)g_tiles * a.g_box_bytes;
+            const uint32_t tx_bytes = (uint32_t)r_loads * a.TH * a.TW * 128 + (uint32_t)g_tiles * (a.nbw / 64) * a.g_box_bytes;
             mbar_arrive_expect_tx(&full[stage], tx_bytes);
             // R tile: one TMA per tile row so that rows land with pitch P (halo columns stay zero).  Paired mode:
             // block 0 holds the tile one row later (row q+1 = pixel q), block 1 holds it in place.
@@ -164,6 +167,8 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
             uint8_t* gt = st + 2 * a.r_blk_bytes;
             if (a.mode == 0) {
               tma_load_4d(&maps.g[gsrc], &full[stage], gt, gc0, x0 - a.pad, y0 - a.pad, n);
+              if (a.nbw == 128)
+                tma_load_4d(&maps.g[gsrc], &full[stage], gt + a.g_tile_bytes, gc0 + 64, x0 - a.pad, y0 - a.pad, n);
             } else {
               for (int t = 0; t < a.taps; ++t)
                 tma_load_4d(&maps.g[t], &full[stage], gt + t * a.g_tile_bytes, gc0, x0, y0, n);
@@ -178,15 +183,16 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
   } else if (warp == 1) {
     // The whole warp runs the control flow so that every address / descriptor is warp-uniform (lives in uniform
     // registers, no per-MMA R2UR/ELECT sequences); one elected lane issues the tcgen05 instructions.
-    constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);  // both operands MN-major
+    const uint32_t idesc = umma_idesc_bf16(128, a.nbw, 1, 1);  // both operands MN-major
     constexpr uint32_t idesc_bias = umma_idesc_bf16(128, 16, 1, 1);
     const uint64_t hi_r = umma_desc_hi_sw128(a.r_blk_bytes, 1024);
-    const uint64_t hi_g = umma_desc_hi_sw128(a.r_blk_bytes, 1024);  // N <= 64: a single block, LBO unused
-    const uint64_t ones_desc = umma_desc(hi_g, smem_u32(ones));
+    const uint64_t hi_g = umma_desc_hi_sw128(a.g_tile_bytes, 1024);  // LBO = distance of the second 64-channel sub-tile
+    const uint64_t ones_desc = umma_desc(umma_desc_hi_sw128(a.r_blk_bytes, 1024), smem_u32(ones));
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
     const int ksteps = a.kt_rows / 16;
+    const int nbw = a.nbw;
     const uint32_t stage_bytes = a.stage_bytes, r_blk_bytes = a.r_blk_bytes;
     const int n_stages = a.stages;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x)
@@ -227,7 +233,7 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
             for (int j = 0; j < 6; ++j) {
               if (j < ntap) {
                 const uint64_t g_desc = g_desc0 + goff[j];
-                const uint32_t d = tmem_base + j * 64;
+                const uint32_t d = tmem_base + j * nbw;
                 // one K step = 16 pixel rows = 2048 B = 128 in the descriptor's (address >> 4) field
                 umma_bf16(d, r_desc, g_desc, idesc, accum);
 #pragma unroll 4
@@ -280,11 +286,11 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
             tap = w.tap0 + j;
             m = w.mb * 128 + row;
           }
-          float* out = a.ws + (((long long)w.split * a.taps + tap) * a.m_pad + m) * a.n_pad + w.nb * 64;
+          float* out = a.ws + (((long long)w.split * a.taps + tap) * a.m_pad + m) * a.n_pad + w.nb * a.nbw;
 #pragma unroll 1
-          for (int col0 = 0; col0 < 64; col0 += 32) {
+          for (int col0 = 0; col0 < a.nbw; col0 += 32) {
             uint32_t v[32];
-            tmem_ld_32x32(tmem_base + j * 64 + col0 + (uint32_t(quarter * 32) << 16), v);
+            tmem_ld_32x32(tmem_base + j * a.nbw + col0 + (uint32_t(quarter * 32) << 16), v);
             tmem_ld_wait();
             if (live) {
 #pragma unroll
@@ -327,7 +333,7 @@ __global__ void wgrad_umma_reduce_kernel(const float* __restrict__ ws, int split
   const int nl = threadIdx.x & 31, t = threadIdx.x >> 5;
   const int n = n0 + nl;
   if (t < taps && n < n_total) {
-    const int np = n < c_src0 ? n : n_blks0 * 64 + (n - c_src0);
+    const int np = n < c_src0 ? n : n_blks0 + (n - c_src0);  // n_blks0 = padded width of source 0 here
     float s = 0.f;
     for (int i = 0; i < splits; ++i) s += ws[(((long long)i * taps + t) * m_pad + m) * n_pad + np];
     tile[nl * taps + t] = s;
@@ -343,6 +349,11 @@ __global__ void wgrad_umma_reduce_kernel(const float* __restrict__ ws, int split
 }
 
 // ------------------------------------------------------------------ host side
+// N = 128 variant: measured on B200 slightly SLOWER than N = 64 with two tap groups (0.422 vs 0.407 ms on 256->256 @100^2,
+// 1.30 vs 1.16 ms on 1024->512 @54^2): the kernel is fed from L2, not MMA-rate-bound, and three passes need smaller
+// tiles.  Kept for experiments: B200UNET_WGRAD_N128=1 enables it.
+static int g_wgrad_n128 = getenv("B200UNET_WGRAD_N128") ? 1 : 0;
+
 struct WgPlan {
   WgArgs a;
   size_t ws_bytes, ws_bias_bytes;
@@ -382,18 +393,22 @@ static bool wg_make_plan(int mode, int Ho, int Wo, int n_img, int m_total, int n
   a.n_img = n_img;
   a.g_c[0] = c_src0;
   a.g_c[1] = n_total - c_src0;
-  a.n_blks0 = (c_src0 + 63) / 64;
-  a.n_blks = a.n_blks0 + (mode == 0 ? (a.g_c[1] + 63) / 64 : 0);
+  a.paired = (mode == 0 && taps == 9 && m_total <= 64) ? 1 : 0;
+  // N = 128 blocks (MMA at the full rate instead of the shared-memory-bound 2/3 of N = 64) when every source is a
+  // multiple of 128 channels; the 3x3 then runs as three tap groups (one filter row each: 3 x 128 TMEM columns)
+  a.nbw = (g_wgrad_n128 && mode == 0 && taps == 9 && !a.paired && c_src0 % 128 == 0 && (n_total - c_src0) % 128 == 0) ? 128 : 64;
+  a.n_blks0 = (c_src0 + a.nbw - 1) / a.nbw;
+  a.n_blks = a.n_blks0 + (mode == 0 ? (a.g_c[1] + a.nbw - 1) / a.nbw : 0);
   a.m_blks = (m_total + 127) / 128;
   a.r_blocks = m_total > 64 ? 2 : 1;
-  a.paired = (mode == 0 && taps == 9 && m_total <= 64) ? 1 : 0;
   a.bias = (want_bias && mode == 0) ? 1 : 0;
-  a.tap_groups = (taps == 9 && !a.paired) ? 2 : 1;
+  a.tap_groups = (taps == 9 && !a.paired) ? (a.nbw == 128 ? 3 : 2) : 1;
   a.m_pad = a.m_blks * 128;
-  a.n_pad = a.n_blks * 64;
-  const int g_tiles = mode == 1 ? taps : 1;
+  a.n_pad = a.n_blks * a.nbw;
+  const int g_tiles = mode == 1 ? taps : (a.nbw / 64);
   const int r_loads = a.paired ? 2 : a.r_blocks;
-  const double mma_groups = a.paired ? 6.0 : (taps == 9 ? 4.5 : (double)taps);
+  const double mma_groups = a.paired ? 6.0 : (taps == 9 ? (a.nbw == 128 ? 3.0 : 4.5) : (double)taps);
+  const double mma_cycles = a.nbw == 128 ? 64.0 : 48.0;
   const double passes = a.tap_groups;
   // tile geometry: kt_rows (multiple of 16) K rows per tile
   double best = 1e30;
@@ -412,7 +427,7 @@ static bool wg_make_plan(int mode, int Ho, int Wo, int n_img, int m_total, int n
       const long long tiles = (long long)((Wo + TW - 1) / TW) * ((Ho + TH - 1) / TH) * n_img;
       // per tile and pass: MMA time ~ MMA groups * K steps * ~48 cycles (shared-memory-bound N = 64 MMA), load time ~
       // bytes moved L2 -> SMEM at ~32 B/cycle/SM; whichever is larger, plus a fixed per-tile cost
-      const double t_mma = mma_groups * (kt / 16) * 48.0;
+      const double t_mma = mma_groups * (kt / 16) * mma_cycles;
       const double t_load = ((double)r_loads * TH * TW * 128 + (double)g_tiles * (TH + a.halo) * P * 128) / 32.0;
       const double cost = (double)tiles * passes * ((t_mma > t_load ? t_mma : t_load) + 300.0);
       if (cost < best) {
@@ -490,7 +505,7 @@ static int wg_launch(const WgMaps& maps, WgPlan& pl, float* dw, float* db, int c
   if (r) return r;
   dim3 grid((unsigned)((pl.a.n_total + 31) / 32), (unsigned)pl.a.m_total);
   wgrad_umma_reduce_kernel<<<grid, 32 * 9, 0, st>>>(pl.a.ws, pl.a.splits, pl.a.taps, pl.a.m_total, pl.a.n_total,
-                                                   pl.a.m_pad, pl.a.n_pad, c_src0, pl.a.n_blks0, dw,
+                                                   pl.a.m_pad, pl.a.n_pad, c_src0, pl.a.n_blks0 * pl.a.nbw, dw,
                                                    pl.a.bias ? pl.a.ws_bias : nullptr, pl.a.bias ? db : nullptr);
   return check_launch("wgrad_umma_reduce");
 }
