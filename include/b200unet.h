@@ -221,6 +221,10 @@ int b200unet_head_ce_bwd(const b200_view* x, const float* w, const float* b, int
 /* ---- boundary transforms */
 int b200unet_nchw_f32_to_nhwc_bf16(const float* src, const b200_view* dst, void* stream);
 int b200unet_nhwc_bf16_to_nchw_f32(const b200_view* src, float* dst, void* stream);
+/* First-layer helper: dst[n,y,x, c*9 + r*3 + s] = src[n, y+r-pad, x+s-pad, c] (zero outside and in the padding channels);
+ * dst.c >= 9*src.c, multiple of 8.  Turns the 1..7-channel first convolution (unet.py:49-52) into a 1x1 problem so that it and
+ * its backward-weights run on the tensor-core kernels. */
+int b200unet_im2col3x3(const b200_view* src, const b200_view* dst, int pad, void* stream);
 /* out[c] = sum over n,h,w of dz (fp32 [c]); workspace b200unet_bn_workspace_bytes(c) */
 int b200unet_channel_sum(const b200_view* dz, float* out, void* workspace, size_t workspace_bytes, void* stream);
 /* y = (mask > 0) ? x : 0, in place allowed; mask laid out like y */

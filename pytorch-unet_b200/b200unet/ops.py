@@ -29,6 +29,11 @@ def workspace(nbytes: int, device) -> torch.Tensor:
     return ws
 
 
+def tensor_cores_available() -> bool:
+    """True on an sm_100 device (the tcgen05 kernels can run)."""
+    return bool(_lib.load().b200unet_device_ok())
+
+
 def _nhwc_empty(n, h, w, c, device) -> torch.Tensor:
     return torch.empty((n, h, w, c), dtype=torch.bfloat16, device=device)
 
@@ -51,6 +56,16 @@ def to_nchw(x: torch.Tensor) -> torch.Tensor:
     v = view(x)
     check(_lib.load().b200unet_nhwc_bf16_to_nchw_f32(C.byref(v), y.data_ptr(), stream_ptr()), "nhwc_bf16_to_nchw_f32")
     return y
+
+
+def im2col3x3(x: torch.Tensor, pad: int) -> torch.Tensor:
+    """First-layer patches: [N,H,W,Cin] (Cin <= 7) -> [N,Ho,Wo,Kp], channel c*9 + r*3 + s, Kp = roundup(9*Cin, 16)."""
+    n, h, w, c = x.shape
+    kp = (9 * c + 15) // 16 * 16
+    out = _nhwc_empty(n, h + 2 * pad - 2, w + 2 * pad - 2, kp, x.device)
+    vx, vo = view(x), view(out)
+    check(_lib.load().b200unet_im2col3x3(C.byref(vx), C.byref(vo), pad, stream_ptr()), "im2col3x3")
+    return out
 
 
 def pack_conv_weight(w: torch.Tensor, src_c: Sequence[int], mode: int) -> torch.Tensor:

@@ -210,6 +210,10 @@ class UNet(nn.Module):
         w, b = P[name + ".weight"], P[name + ".bias"]
         return ops.conv_fwd(srcs, w.detach(), b.detach(), pad, relu, impl=self.conv_impl)
 
+    def _first_layer_patches(self, prefix: str, srcs, w) -> bool:
+        return (prefix == "down_path.0" and self.conv_impl == ops.IMPL_AUTO and len(srcs) == 1
+                and srcs[0].shape[3] * 9 <= 64 and w.shape[0] % 16 == 0 and ops.tensor_cores_available())
+
     def _block_forward(self, prefix: str, blk: UNetConvBlock, srcs, P, tape):
         """UNetConvBlock.forward (unet.py:104-106).  Returns (output, post-ReLU activation of the 2nd conv)."""
         pad = int(self.padding)
@@ -305,7 +309,17 @@ class UNet(nn.Module):
             srcs = rec["srcs"] if i == 0 else [rec["o0"]]
             dw = self._new_grad(names[i] + ".weight", w)
             db = self._new_grad(names[i] + ".bias", P[names[i] + ".bias"])
-            ops.conv_wgrad(dz, srcs, 3, pad, impl=self.conv_impl, dw=dw, db=db)
+            if i == 0 and self._first_layer_patches(prefix, srcs, w):
+                # 1..7 input channels: the 3x3 patch (9*Cin values) fits one 64-wide K chunk, so backward-weights of
+                # the first layer runs as a 1x1 problem on the tensor-core kernel over the im2col'ed image (built here,
+                # 2*Kp bytes per pixel, dropped right after).  Measured 0.77 ms vs 1.24 ms for the CUDA-core kernel at
+                # batch 32; the forward stays on the CUDA-core first-layer kernel (0.70 ms vs 0.81 ms through im2col).
+                patches = ops.im2col3x3(srcs[0], pad)
+                dw1, _ = ops.conv_wgrad(dz, [patches], 1, 0, impl=self.conv_impl, db=db)
+                dw.copy_(dw1[:, :w.shape[1] * 9, 0, 0].reshape(w.shape))
+                del patches
+            else:
+                ops.conv_wgrad(dz, srcs, 3, pad, impl=self.conv_impl, dw=dw, db=db)
             grads[names[i] + ".weight"], grads[names[i] + ".bias"] = dw, db
             if i == 1:
                 g = torch.empty_like(rec["o0"])

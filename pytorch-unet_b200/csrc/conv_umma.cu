@@ -17,10 +17,12 @@
 //
 // B operand: packed weights [Cout][tap][kpad] (K-major), one TMA box {64, BN} per (tap, chunk).
 //
-// Warp roles (7 warps, 1 CTA / SM, persistent over tiles): 0 = A producer, 1 = B producer, 2 = TMEM allocator +
-// single-thread tcgen05.mma issuer, 3..6 = epilogue (tcgen05.ld -> bias / ReLU / mask -> bf16 -> global).
+// Warp roles (11 warps, 1 CTA / SM, persistent over tiles): 0 = A producer, 1 = B producer, 2 = TMEM allocator +
+// tcgen05.mma issuer (warp-uniform control flow, one elected lane issues), 3..10 = epilogue (two warps per TMEM lane
+// quarter; bias pre-loaded into the accumulator with tcgen05.st, tcgen05.ld -> cvt.relu.bf16x2 -> per-warp shared
+// memory transpose -> mask -> full-line global stores).
 // Accumulators: MB x BN fp32 columns in TMEM, double-buffered when 2*MB*BN <= 512 so the epilogue of tile i overlaps
-// the MMAs of tile i+1.
+// the MMAs of tile i+1.  Optional CTA pairs (cluster of 2) fetch half of every weight tile each and multicast it.
 #include <cstdlib>
 
 #include "conv_impl.h"
@@ -29,11 +31,12 @@
 
 namespace b200 {
 
-constexpr int kUmmaThreads = 224;
+constexpr int kUmmaThreads = 352;  // 3 control warps + 8 epilogue warps (two per TMEM lane quarter)
+constexpr int kEpiWarps = 8;
 constexpr int kNA = 2;        // A (activation tile) stages
 constexpr int kMaxNB = 8;     // B (weight tile) stages
 constexpr uint32_t kSmemBudget = 188 * 1024;   // A + B stages
-constexpr uint32_t kStageOutBytes = 4 * 8192;  // epilogue transpose buffers: 4 warps x [32 rows][64 cols] fp32
+constexpr uint32_t kStageOutBytes = kEpiWarps * 4096;  // epilogue transpose buffers: per warp [32 rows][64 cols] bf16
 
 struct TileMaps {
   CUtensorMap a[4];
@@ -122,7 +125,7 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&t_full[i], 1);
-      mbar_init(&t_empty[i], 4);
+      mbar_init(&t_empty[i], kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -198,10 +201,10 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     const uint32_t a_stage_bytes = a.a_stage_bytes;
     for (int tile = work0; tile < total_tiles; tile += work_step, ++it) {
       const int buf = it % NBUF;
-      mbar_wait(&t_empty[buf], ((it / NBUF) & 1) ^ 1);
+      mbar_wait(&t_empty[buf], (it / NBUF) & 1);  // epilogue hands every buffer over, also before its first use
       tc_fence_after_sync();
       const uint32_t acc = tmem_base + buf * (MB * BN);
-      uint32_t accum = 0;
+      uint32_t accum = a.bias ? 1u : 0u;  // with a bias the epilogue warps pre-loaded it into the accumulator
       for (int s = 0; s < a.num_a; ++s) {
         for (int c0 = 0; c0 < a.a_c[s]; c0 += 64) {
           mbar_wait(&a_full[astage], aphase);
@@ -256,18 +259,61 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     }
   } else {
     // ================= epilogue: 4 warps, warp w owns TMEM lanes 32*(w%4) .. +31 (= 32 output positions).
-    // tcgen05.ld gives every lane one position's row of accumulators, but a row-per-lane store touches 32 different
-    // 128-byte lines per instruction (measured: the old epilogue, not the MMAs, bounded the 64/128-channel layers).
-    // So each warp transposes through its own 8 KiB shared-memory buffer ([32 rows][CP cols] fp32, 16-byte chunks
-    // XOR-swizzled by row): after the transpose CP/8 consecutive lanes own one position's contiguous CP*2 bytes, and
-    // bias / ReLU / mask / bf16 conversion happen on that side, so mask loads and output stores are full lines.
+    // Measured: with a row-per-lane store, and then with fp32 bias/ReLU math on the store side, the 64-channel layers
+    // were bound by this epilogue's instruction count (~1.4 TB/s of output), not by the MMAs.  So:
+    //  * the bias is PRE-LOADED into the TMEM accumulator (tcgen05.st) before the tile's first MMA, which then
+    //    accumulates from the start: no FADD per element;
+    //  * ReLU is the .relu modifier of the fp32 -> bf16x2 conversion: no FMNMX per element;
+    //  * the converted row goes through a per-warp shared-memory transpose (16-byte chunks XOR-swizzled by row) so that
+    //    CP/8 consecutive lanes own one position's contiguous CP*2 bytes: mask loads and stores are full lines.
     constexpr int CP = BN < 64 ? BN : 64;   // columns per pass
     constexpr int LPR = CP / 8;             // lanes per row on the store side (one 16-byte bf16 chunk each)
     constexpr int RPI = 32 / LPR;           // rows per store iteration
-    constexpr int CH16 = CP / 4;            // 16-byte fp32 chunks per staged row
-    const int quarter = warp & 3;
-    float* stg = reinterpret_cast<float*>(sOut + quarter * 8192);
+    const int quarter = warp & 3;     // TMEM lane quarter this warp may access
+    const int egrp = (warp - 3) >> 2;  // two warps share a quarter: they split the (M-block, column pass) work items
+    uint4* stg = reinterpret_cast<uint4*>(sOut + (warp - 3) * 4096);   // [32 rows][LPR chunks] of 16 B
     const int rsub = lane / LPR, cch = lane % LPR;
+    const uint32_t lane_base = uint32_t(quarter * 32) << 16;
+
+    // writes bias[n0 .. n0+BN) into the rows of accumulator buffer `buf` — each warp exactly the (M-block, column
+    // pass) regions it drains itself, so a fast warp never overwrites a region its partner is still reading
+    constexpr int PASSES = BN / CP;
+    auto preload_bias = [&](int tile, int buf) {
+      if (a.bias == nullptr) return;
+      const TileCoord t = decode_tile<CL>(a, tile, rank, BN);
+      const int d = a.ndst > 1 ? min(t.n0 / a.dst_c0, a.ndst - 1) : 0;
+      const float* bp = a.bias + (t.n0 - d * a.dst_c0);
+#pragma unroll 1
+      for (int wi = egrp; wi < MB * PASSES; wi += 2) {
+        const int mb = wi / PASSES;
+        const int c0 = (wi - mb * PASSES) * CP;
+#pragma unroll 1
+        for (int col0 = c0; col0 < c0 + CP; col0 += 32) {
+          uint32_t bv[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t.n0 + col0 + 4 * j < a.cout_total) f = *reinterpret_cast<const float4*>(bp + col0 + 4 * j);
+            bv[4 * j] = __float_as_uint(f.x);
+            bv[4 * j + 1] = __float_as_uint(f.y);
+            bv[4 * j + 2] = __float_as_uint(f.z);
+            bv[4 * j + 3] = __float_as_uint(f.w);
+          }
+          tmem_st_32x32(tmem_base + buf * (MB * BN) + mb * BN + col0 + lane_base, bv);
+        }
+      }
+      tmem_st_wait();
+    };
+
+    // hand the (pre-loaded) buffers of the first NBUF tiles to the MMA warp
+    for (int b = 0; b < NBUF; ++b) {
+      const int tile = work0 + b * work_step;
+      if (tile < total_tiles) preload_bias(tile, b);
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[b]);
+    }
+
     int it = 0;
     for (int tile = work0; tile < total_tiles; tile += work_step, ++it) {
       const TileCoord t = decode_tile<CL>(a, tile, rank, BN);
@@ -278,16 +324,17 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       const int ch0 = t.n0 - d * a.dst_c0;
       const DView& dst = a.dst[d];
       const bf16* mk = a.mask[d];
-#pragma unroll
-      for (int mb = 0; mb < MB; ++mb) {
+#pragma unroll 1  // keep the epilogue body small: fully unrolled it was ~3000 instructions and ran out of the I-cache
+      for (int wi = egrp; wi < MB * PASSES; wi += 2) {
+        const int mb = wi / PASSES;
+        const int col0 = (wi - mb * PASSES) * CP;
         const int q = mb * 128 + quarter * 32 + lane;
         const int ty = q / a.P, tx = q - ty * a.P;
         const int oy = t.y0 + ty, ox = t.x0 + tx;
         const bool valid = ty < a.TH && tx < a.TW && oy < a.Ho && ox < a.Wo;
         const long long off = valid ? dst.off(t.n, oy, ox) + ch0 : -1;  // -1 = nothing to store for this position
-        const uint32_t taddr = tmem_base + buf * (MB * BN) + mb * BN + (uint32_t(quarter * 32) << 16);
-#pragma unroll 1
-        for (int col0 = 0; col0 < BN; col0 += CP) {
+        const uint32_t taddr = tmem_base + buf * (MB * BN) + mb * BN + lane_base;
+        {
           uint32_t v[CP];
           {
             uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
@@ -298,61 +345,58 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
             }
           }
           tmem_ld_wait();
-          // row-owner side: lane writes its position's CP accumulators (16-byte chunk j goes to slot j ^ (lane & 15))
+          // row-owner side: convert this position's CP accumulators (ReLU folded into the conversion) and park them as
+          // LPR 16-byte chunks; chunk j goes to slot j ^ (lane & (LPR-1)) so the 32 rows do not collide on banks
 #pragma unroll
-          for (int j = 0; j < CH16; ++j) {
-            const int slot = (j ^ (lane & (CH16 - 1)));
-            *reinterpret_cast<uint4*>(stg + lane * CP + slot * 4) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          for (int j = 0; j < LPR; ++j) {
+            uint4 c;
+            if (a.relu) {
+              c.x = pack_bf16x2_relu(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+              c.y = pack_bf16x2_relu(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+              c.z = pack_bf16x2_relu(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+              c.w = pack_bf16x2_relu(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+            } else {
+              c.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+              c.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+              c.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+              c.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+            }
+            stg[lane * LPR + (j ^ (lane & (LPR - 1)))] = c;
           }
           __syncwarp();
-          // store side: this lane's 8 columns are fixed for the pass
+          // store side: lane (rsub, cch) moves chunk cch of rows rsub, rsub + RPI, ...
           const int col = col0 + cch * 8;
           const bool col_ok = t.n0 + col < a.cout_total;
-          float bv[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) bv[j] = 0.f;
-          if (a.bias && col_ok) {
-            const float4 b0 = *reinterpret_cast<const float4*>(a.bias + ch0 + col);
-            const float4 b1 = *reinterpret_cast<const float4*>(a.bias + ch0 + col + 4);
-            bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w;
-            bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
-          }
-          // phase A: all row offsets and (dgrad) all mask vectors of the pass first, so the global loads overlap
           long long offs[LPR];
           bf16x8 mv[LPR];
 #pragma unroll
           for (int i = 0; i < LPR; ++i) {
             offs[i] = __shfl_sync(0xffffffffu, off, i * RPI + rsub);
             if (!col_ok) offs[i] = -1;
-            mv[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
             if (mk && offs[i] >= 0) mv[i] = *reinterpret_cast<const bf16x8*>(mk + offs[i] + col);
           }
-          // phase B: bias / ReLU / mask / convert / store, one contiguous 16-byte chunk per lane and row
 #pragma unroll
           for (int i = 0; i < LPR; ++i) {
             const int R = i * RPI + rsub;
             if (offs[i] >= 0) {
-              const int s0 = ((2 * cch) ^ (R & (CH16 - 1))), s1 = ((2 * cch + 1) ^ (R & (CH16 - 1)));
-              const float4 f0 = *reinterpret_cast<const float4*>(stg + R * CP + s0 * 4);
-              const float4 f1 = *reinterpret_cast<const float4*>(stg + R * CP + s1 * 4);
-              float f[8] = {f0.x + bv[0], f0.y + bv[1], f0.z + bv[2], f0.w + bv[3],
-                            f1.x + bv[4], f1.y + bv[5], f1.z + bv[6], f1.w + bv[7]};
-              if (a.relu) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
-              }
-              if (mk) {
-                float m[8];
+              uint4 c = stg[R * LPR + (cch ^ (R & (LPR - 1)))];
+              if (mk) {  // dgrad: zero where the producer's ReLU was inactive (mask <= 0)
+                float f[8], m[8];
+                unpack8(c, f);
                 unpack8(mv[i], m);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[j] = m[j] > 0.f ? f[j] : 0.f;
+                c = pack8(f);
               }
-              *reinterpret_cast<bf16x8*>(dst.p + offs[i] + col) = pack8(f);
+              *reinterpret_cast<uint4*>(dst.p + offs[i] + col) = c;
             }
           }
           __syncwarp();
         }
       }
+      // this buffer's next user is tile + NBUF * work_step: pre-load its bias, then hand the buffer back
+      const int next = tile + NBUF * work_step;
+      if (next < total_tiles) preload_bias(next, buf);
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[buf]);

@@ -104,6 +104,36 @@ __global__ void pack_convt_kernel(const float* __restrict__ w, bf16* __restrict_
   }
 }
 
+// ------------------------------------------------------------------ first-layer im2col
+// dst[n, y, x, c*9 + r*3 + s] = src[n, y + r - pad, x + s - pad, c] (zero outside / for the padding channels).
+// With 1..7 input channels the 3x3 patch (9..63 values) fits one 64-wide K chunk, so the first convolution and its
+// backward-weights become 1x1 problems for the tensor-core kernels; the patch tensor costs 2*Kp bytes per pixel.
+__global__ void im2col3x3_kernel(DView src, DView dst, int pad) {
+  const long long total = (long long)dst.n * dst.h * dst.w;
+  const int kp = dst.c, cin = src.c;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(p % dst.w);
+    const long long t = p / dst.w;
+    const int oy = (int)(t % dst.h), n = (int)(t / dst.h);
+    bf16* o = dst.p + dst.off(n, oy, ox);
+    for (int j0 = 0; j0 < kp; j0 += 8) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int q = j0 + j;
+        float v = 0.f;
+        if (q < 9 * cin) {
+          const int c = q / 9, tap = q - c * 9;
+          const int iy = oy + tap / 3 - pad, ix = ox + tap % 3 - pad;
+          if (iy >= 0 && iy < src.h && ix >= 0 && ix < src.w) v = bf2f(src.p[src.off(n, iy, ix) + c]);
+        }
+        f[j] = v;
+      }
+      *reinterpret_cast<bf16x8*>(o + j0) = pack8(f);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ y = mask > 0 ? x : 0
 __global__ void relu_mask_kernel(DView x, DView m, DView y) {
   const long long total = (long long)x.n * x.h * x.w * x.c;
@@ -159,6 +189,15 @@ int b200unet_nhwc_bf16_to_nchw_f32(const b200_view* src, float* dst, void* strea
   dim3 grid((unsigned)((total + 31) / 32), (unsigned)((src->c + 31) / 32));
   nhwc_to_nchw_kernel<<<grid, dim3(32, 32), 0, as_stream(stream)>>>(dview(*src), dst);
   return check_launch("nhwc_to_nchw");
+}
+
+int b200unet_im2col3x3(const b200_view* src, const b200_view* dst, int pad, void* stream) {
+  B200_REQUIRE(view_ok(src) && view_ok(dst), "im2col3x3: bad views");
+  B200_REQUIRE(dst->n == src->n && dst->h == src->h + 2 * pad - 2 && dst->w == src->w + 2 * pad - 2,
+               "im2col3x3: dst extent must be the 3x3 convolution's output extent");
+  B200_REQUIRE(dst->c % 8 == 0 && dst->c >= 9 * src->c && vec8_ok(*dst), "im2col3x3: dst needs >= 9*cin channels, multiple of 8");
+  im2col3x3_kernel<<<grid_for(view_pixels(*dst), 256), 256, 0, as_stream(stream)>>>(dview(*src), dview(*dst), pad);
+  return check_launch("im2col3x3");
 }
 
 static int conv_kpad(int num_src, const int* src_c) {
