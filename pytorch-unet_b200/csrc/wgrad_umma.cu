@@ -171,7 +171,8 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
                 tma_load_4d(&maps.g[gsrc], &full[stage], gt + a.g_tile_bytes, gc0 + 64, x0 - a.pad, y0 - a.pad, n);
             } else {
               for (int t = 0; t < a.taps; ++t)
-                tma_load_4d(&maps.g[t], &full[stage], gt + t * a.g_tile_bytes, gc0, x0, y0, n);
+                for (int h = 0; h < a.nbw / 64; ++h)
+                  tma_load_4d(&maps.g[t], &full[stage], gt + (t * (a.nbw / 64) + h) * a.g_tile_bytes, gc0 + h * 64, x0, y0, n);
             }
             if (++stage == a.stages) {
               stage = 0;
@@ -213,7 +214,7 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
               const int r = tap / a.kx, sx = tap - r * a.kx;
               o = (uint32_t)(r * a.P + sx) * 8;
             } else {
-              o = (uint32_t)(w.tap0 + j) * (a.g_tile_bytes >> 4);
+              o = (uint32_t)(w.tap0 + j) * (a.nbw / 64) * (a.g_tile_bytes >> 4);
             }
           }
           goff[j] = o;
@@ -397,6 +398,9 @@ static bool wg_make_plan(int mode, int Ho, int Wo, int n_img, int m_total, int n
   // N = 128 blocks (MMA at the full rate instead of the shared-memory-bound 2/3 of N = 64) when every source is a
   // multiple of 128 channels; the 3x3 then runs as three tap groups (one filter row each: 3 x 128 TMEM columns)
   a.nbw = (g_wgrad_n128 && mode == 0 && taps == 9 && !a.paired && c_src0 % 128 == 0 && (n_total - c_src0) % 128 == 0) ? 128 : 64;
+  // ConvTranspose: every dy element feeds exactly one tap, so operand reuse is low (43 MAC per loaded byte with N = 64)
+  // and the kernel is fed from L2: N = 128 (4 taps x 128 = all 512 TMEM columns) more than doubles the reuse
+  if (mode == 1 && n_total % 128 == 0) a.nbw = 128;
   a.n_blks0 = (c_src0 + a.nbw - 1) / a.nbw;
   a.n_blks = a.n_blks0 + (mode == 0 ? (a.g_c[1] + a.nbw - 1) / a.nbw : 0);
   a.m_blks = (m_total + 127) / 128;
@@ -405,7 +409,7 @@ static bool wg_make_plan(int mode, int Ho, int Wo, int n_img, int m_total, int n
   a.tap_groups = (taps == 9 && !a.paired) ? (a.nbw == 128 ? 3 : 2) : 1;
   a.m_pad = a.m_blks * 128;
   a.n_pad = a.n_blks * a.nbw;
-  const int g_tiles = mode == 1 ? taps : (a.nbw / 64);
+  const int g_tiles = (mode == 1 ? taps : 1) * (a.nbw / 64);
   const int r_loads = a.paired ? 2 : a.r_blocks;
   const double mma_groups = a.paired ? 6.0 : (taps == 9 ? (a.nbw == 128 ? 3.0 : 4.5) : (double)taps);
   const double mma_cycles = a.nbw == 128 ? 64.0 : 48.0;
@@ -413,7 +417,7 @@ static bool wg_make_plan(int mode, int Ho, int Wo, int n_img, int m_total, int n
   // tile geometry: kt_rows (multiple of 16) K rows per tile
   double best = 1e30;
   bool found = false;
-  for (int kt = 64; kt <= 256; kt += 16) {
+  for (int kt = 32; kt <= 256; kt += 16) {
     for (int P = a.halo + 1; P <= 256 && P <= Wo + a.halo + 8; ++P) {
       const int TW = P - a.halo;
       int TH = (kt - a.paired) / P;
