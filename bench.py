@@ -321,8 +321,14 @@ def run_ours(args):
     ms3 = sum(v["ms"] for v in k3.values()) / args.steps
     achieved = fl3 / (ms3 * 1e-3) / 1e12 if ms3 > 0 else 0.0
     calls3 = sum(v["calls"] for v in k3.values()) / args.steps
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.isfile(tpath):  # ncu dram__bytes_read+write per tcgen05 launch of the same bench command (batch 32)
+        with open(tpath) as fh:
+            traffic = json.load(fh).get("dram_bytes_per_launch")
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved / peak_tf, "traffic": None,
+                "frac": achieved / peak_tf, "traffic": traffic,
+                "traffic_note": "mean DRAM bytes per tcgen05 launch (ncu, profiles/r01_traffic.json)",
                 "kernel": "umma_conv_kernel + wgrad_umma_kernel (all 3x3 conv fprop/dgrad/wgrad launches of a step)",
                 "peak_source": f"{which} bf16_tflops_sustained", "flops_per_step": fl3, "ms_per_step_in_kernel": ms3,
                 "launches_per_step": calls3,

@@ -115,64 +115,47 @@ maxpool_bwd_kernel(DView dy, const uint8_t* __restrict__ idx8, DView dx, DView a
         code[0] = idx8[opix * dy.c + l];
       }
     }
-    // phase 1: issue every load of the window (skip-gradient window and ReLU mask of the four positions) before any
-    // store — `add` may alias `dx`, so the compiler cannot hoist them across the stores on its own
-    float av[4][VEC], mv[4][VEC];
-    bool live[4];
-    long long offs[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int ih = 2 * oh + (k >> 1), iw = 2 * ow + (k & 1);
-      live[k] = ih < dx.h && iw < dx.w;
-      offs[k] = live[k] ? dx.off(n, ih, iw) + l * VEC : 0;
+    for (int a = 0; a < 2; ++a)
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        av[k][j] = 0.f;
-        mv[k][j] = 1.f;
-      }
-      if (!live[k]) continue;
-      const int ay = ih - add_y, ax = iw - add_x;
-      if (has_add && ay >= 0 && ay < add.h && ax >= 0 && ax < add.w) {
-        const bf16* sp = add.p + add.off(n, ay, ax) + l * VEC;
+      for (int b = 0; b < 2; ++b) {
+        const int ih = 2 * oh + a, iw = 2 * ow + b;
+        if (ih >= dx.h || iw >= dx.w) continue;
+        float r[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) r[j] = (code[j] == a * 2 + b) ? g[j] : 0.f;
+        const int ay = ih - add_y, ax = iw - add_x;
+        if (has_add && ay >= 0 && ay < add.h && ax >= 0 && ax < add.w) {
+          const bf16* s = add.p + add.off(n, ay, ax) + l * VEC;
+          if (VEC == 8) {
+            float t[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(s), t);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) r[j] += t[j];
+          } else {
+            r[0] += bf2f(s[0]);
+          }
+        }
+        const long long o = dx.off(n, ih, iw) + l * VEC;
+        if (mask) {
+          if (VEC == 8) {
+            float t[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(mask + o), t);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) r[j] = t[j] > 0.f ? r[j] : 0.f;
+          } else {
+            r[0] = bf2f(mask[o]) > 0.f ? r[0] : 0.f;
+          }
+        }
         if (VEC == 8) {
           float t[8];
-          unpack8(*reinterpret_cast<const bf16x8*>(sp), t);
 #pragma unroll
-          for (int j = 0; j < VEC; ++j) av[k][j] = t[j];
+          for (int j = 0; j < VEC; ++j) t[j] = r[j];
+          *reinterpret_cast<bf16x8*>(dx.p + o) = pack8(t);
         } else {
-          av[k][0] = bf2f(sp[0]);
+          dx.p[o] = f2bf(r[0]);
         }
       }
-      if (mask) {
-        if (VEC == 8) {
-          float t[8];
-          unpack8(*reinterpret_cast<const bf16x8*>(mask + offs[k]), t);
-#pragma unroll
-          for (int j = 0; j < VEC; ++j) mv[k][j] = t[j];
-        } else {
-          mv[k][0] = bf2f(mask[offs[k]]);
-        }
-      }
-    }
-    // phase 2: scatter + add + mask, store
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (!live[k]) continue;
-      float r[VEC];
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        r[j] = ((code[j] == k) ? g[j] : 0.f) + av[k][j];
-        r[j] = mv[k][j] > 0.f ? r[j] : 0.f;
-      }
-      if (VEC == 8) {
-        float t[8];
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) t[j] = r[j];
-        *reinterpret_cast<bf16x8*>(dx.p + offs[k]) = pack8(t);
-      } else {
-        dx.p[offs[k]] = f2bf(r[0]);
-      }
-    }
   }
 }
 
