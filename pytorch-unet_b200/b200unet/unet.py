@@ -85,6 +85,7 @@ class _Tape:
         self.pools: List[dict] = []
         self.ups: List[dict] = []
         self.head: dict = {}
+        self.P: Dict[str, torch.Tensor] = {}
 
 
 def _crop_window(bridge: torch.Tensor, h: int, w: int) -> Tuple[torch.Tensor, int, int]:
@@ -161,6 +162,9 @@ class UNet(nn.Module):
         else:
             self.last = nn.Conv2d(prev, n_classes, kernel_size=1)
         self._param_names = [n for n, _ in self.named_parameters()]
+        self._padspec = self._build_padspec(in_channels, n_classes, depth, wf)
+        self._real_shapes = {n: tuple(p.shape) for n, p in self.named_parameters()}
+        self._cur_grads: Dict[str, torch.Tensor] = {}
         # hooks for the data-parallel wrapper: grad arena allocator + "these gradients are final" callback
         self._grad_alloc: Optional[Callable[[str, Tuple[int, ...], torch.device], torch.Tensor]] = None
         self._grad_ready: Optional[Callable[[str], None]] = None
@@ -182,6 +186,92 @@ class UNet(nn.Module):
         params = [p for _, p in self.named_parameters()]
         return _UNetFunction.apply(self, x, labels, *params)
 
+    # ---------------------------------------------------------------- internal channel padding
+    # The tensor-core kernels need NHWC channel counts that are multiples of 8 (TMA strides) and the first-layer
+    # kernels multiples of 16.  Narrow variants (the repo's feature net: wf=2 -> 4 / 8 channels, options.py:19-25)
+    # therefore run with their 4- and 8-channel tensors padded to 16 channels INSIDE the module: parameters are
+    # zero-padded copies made per call, pad channels carry exact zeros through conv/ReLU/BN/pool/upsample, gradients
+    # are un-padded before they are returned.  state_dict, parameter shapes and results are unchanged; for the paper
+    # widths (64..1024) the spec is empty and none of this code runs.
+    @staticmethod
+    def _cpad(c: int) -> int:
+        return c if (c % 8 == 0 and c >= 16) else max(16, (c + 7) // 8 * 8)
+
+    def _build_padspec(self, in_channels, n_classes, depth, wf):
+        spec: Dict[str, tuple] = {}
+        cp = self._cpad
+
+        def conv(name, srcs_real, cout, pad_src=True):
+            srcs_pad = [cp(c) if pad_src else c for c in srcs_real]
+            segs, ro, po = [], 0, 0
+            for r, pd in zip(srcs_real, srcs_pad):
+                segs.append((ro, r, po))
+                ro, po = ro + r, po + pd
+            if cp(cout) != cout or po != ro:
+                spec[name + ".weight"] = ([(0, cout, 0)], cp(cout), segs, po)
+            if cp(cout) != cout:
+                spec[name + ".bias"] = ([(0, cout, 0)], cp(cout), None, None)
+
+        def block(prefix, srcs_real, cout, first=False):
+            i2, b1, b2 = (3, 2, 5) if self.batch_norm else (2, None, None)
+            conv(f"{prefix}.block.0", srcs_real, cout, pad_src=not first)
+            conv(f"{prefix}.block.{i2}", [cout], cout)
+            if self.batch_norm and cp(cout) != cout:
+                for b in (b1, b2):
+                    spec[f"{prefix}.block.{b}.weight"] = ([(0, cout, 0)], cp(cout), None, None)
+                    spec[f"{prefix}.block.{b}.bias"] = ([(0, cout, 0)], cp(cout), None, None)
+
+        prev = in_channels
+        for i in range(depth):
+            block(f"down_path.{i}", [prev], 2 ** (wf + i), first=(i == 0))
+            prev = 2 ** (wf + i)
+        for j, i in enumerate(reversed(range(depth - 1))):
+            skip = 2 ** (wf + i)
+            up_out, blk_out = (skip, skip) if self.up_block == "paper" else (prev, prev)
+            if self.up_mode == "upconv":  # weight [cin, cout, 2, 2]
+                if cp(prev) != prev or cp(up_out) != up_out:
+                    spec[f"up_path.{j}.up.weight"] = ([(0, prev, 0)], cp(prev), [(0, up_out, 0)], cp(up_out))
+                if cp(up_out) != up_out:
+                    spec[f"up_path.{j}.up.bias"] = ([(0, up_out, 0)], cp(up_out), None, None)
+            else:
+                conv(f"up_path.{j}.up.1", [prev], up_out)
+            block(f"up_path.{j}.conv_block", [up_out, skip], blk_out)
+            prev = blk_out
+        if cp(prev) != prev:
+            spec[("last.0" if self.non_neg else "last") + ".weight"] = ([(0, n_classes, 0)], n_classes, [(0, prev, 0)], cp(prev))
+        return spec
+
+    @staticmethod
+    def _pad_tensor(t: torch.Tensor, sp: tuple) -> torch.Tensor:
+        segs0, size0, segs1, size1 = sp
+        shape = list(t.shape)
+        shape[0] = size0
+        if segs1 is not None:
+            shape[1] = size1
+        out = torch.zeros(shape, dtype=t.dtype, device=t.device)
+        for r0, l0, p0 in segs0:
+            if segs1 is None:
+                out[p0:p0 + l0] = t[r0:r0 + l0]
+            else:
+                for r1, l1, p1 in segs1:
+                    out[p0:p0 + l0, p1:p1 + l1] = t[r0:r0 + l0, r1:r1 + l1]
+        return out
+
+    @staticmethod
+    def _unpad_into(dst: torch.Tensor, padded: torch.Tensor, sp: tuple) -> None:
+        segs0, _, segs1, _ = sp
+        for r0, l0, p0 in segs0:
+            if segs1 is None:
+                dst[r0:r0 + l0] = padded[p0:p0 + l0]
+            else:
+                for r1, l1, p1 in segs1:
+                    dst[r0:r0 + l0, r1:r1 + l1] = padded[p0:p0 + l0, p1:p1 + l1]
+
+    def _padded_params(self, P: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        if not self._padspec:
+            return P
+        return {k: (self._pad_tensor(v.detach(), self._padspec[k]) if k in self._padspec else v) for k, v in P.items()}
+
     # ---------------------------------------------------------------- helpers
     def _packed(self, name: str, w: torch.Tensor, mode: int, src_c=None, transposed_conv: bool = False) -> torch.Tensor:
         key = (name, mode)
@@ -196,13 +286,25 @@ class UNet(nn.Module):
         return packed
 
     def _new_grad(self, name: str, like: torch.Tensor) -> torch.Tensor:
+        """Gradient buffer for parameter `name` (`like` has the shape the kernels produce, i.e. the padded one)."""
+        if name in self._padspec:  # kernels write the padded gradient into a scratch tensor, _done() un-pads it
+            return torch.empty(like.shape, dtype=torch.float32, device=like.device)
         if self._grad_alloc is not None:
             return self._grad_alloc(name, tuple(like.shape), like.device)
         return torch.empty(like.shape, dtype=torch.float32, device=like.device)
 
     def _done(self, *names: str) -> None:
-        if self._grad_ready is not None:
-            for n in names:
+        for n in names:
+            if n in self._padspec:
+                real_shape = self._real_shapes[n]
+                padded = self._cur_grads[n]
+                if self._grad_alloc is not None:
+                    real = self._grad_alloc(n, real_shape, padded.device)
+                else:
+                    real = torch.empty(real_shape, dtype=torch.float32, device=padded.device)
+                self._unpad_into(real, padded, self._padspec[n])
+                self._cur_grads[n] = real
+            if self._grad_ready is not None:
                 self._grad_ready(n)
 
     # ---------------------------------------------------------------- forward
@@ -227,15 +329,24 @@ class UNet(nn.Module):
             if blk.batch_norm:
                 bn = blk.bns()[i]
                 g, bt = P[bn_names[i] + ".weight"].detach(), P[bn_names[i] + ".bias"].detach()
+                rm, rv = bn.running_mean, bn.running_var
+                padded_stats = rm is not None and rm.numel() != a.shape[3]
+                if padded_stats:  # internal channel padding: the kernels see padded copies of the running statistics
+                    extra = a.shape[3] - rm.numel()
+                    rm = torch.cat([rm, rm.new_zeros(extra)])
+                    rv = torch.cat([rv, rv.new_ones(extra)])
                 if self.training or bn.running_mean is None:
-                    o, mean, invstd = ops.bn_fwd_train(a, g, bt, bn.running_mean if self.training else None,
-                                                       bn.running_var if self.training else None,
+                    o, mean, invstd = ops.bn_fwd_train(a, g, bt, rm if self.training else None,
+                                                       rv if self.training else None,
                                                        bn.momentum if bn.momentum is not None else 0.1, bn.eps)
+                    if self.training and padded_stats:
+                        bn.running_mean.copy_(rm[:bn.running_mean.numel()])
+                        bn.running_var.copy_(rv[:bn.running_var.numel()])
                     if self.training and bn.num_batches_tracked is not None:
                         bn.num_batches_tracked += 1
                     rec[f"bn{i}"] = (mean, invstd)
                 else:
-                    o = ops.bn_fwd_eval(a, g, bt, bn.running_mean, bn.running_var, bn.eps)
+                    o = ops.bn_fwd_eval(a, g, bt, rm, rv, bn.eps)
                     rec[f"bn{i}"] = None
             else:
                 o = a
@@ -246,6 +357,9 @@ class UNet(nn.Module):
         return rec["o1"], rec["a1"]
 
     def _run_forward(self, x, labels, P, tape):
+        P = self._padded_params(P)
+        if tape is not None:
+            tape.P = P
         if x.dtype != torch.float32:
             x = x.float()
         cur = ops.to_nhwc(x)
@@ -330,7 +444,9 @@ class UNet(nn.Module):
                        names[i] + ".weight", names[i] + ".bias")
 
     def _run_backward(self, tape, P, labels, grad_out) -> Dict[str, torch.Tensor]:
+        P = tape.P
         grads: Dict[str, torch.Tensor] = {}
+        self._cur_grads = grads
         bn = self.batch_norm
         hname = "last.0" if self.non_neg else "last"
         hw, hb = P[hname + ".weight"], P[hname + ".bias"]
@@ -401,4 +517,5 @@ class UNet(nn.Module):
                 g = gp
         if self._grads_done is not None:
             self._grads_done()
+        self._cur_grads = {}
         return grads

@@ -439,7 +439,13 @@ static int pick_bn(int cout_total, int ndst, int dst_c0) {
     const int bn = cands[i];
     if (cout_total % bn == 0 && (ndst == 1 || dst_c0 % bn == 0)) return bn;
   }
-  return ndst == 1 ? 32 : 0;  // partial last N-tile handled by the column predicate
+  // no exact tiling: a partial last N tile is fine (weight rows past Cout are zero-filled by TMA, the epilogue predicates
+  // the columns) as long as no tile straddles two destinations
+  for (int i = 2; i < 4; ++i) {
+    const int bn = cands[i];
+    if (ndst == 1 || dst_c0 % bn == 0) return bn;
+  }
+  return 0;
 }
 
 // Chooses tile geometry (MB M-blocks of 128 positions, pitch P, TH rows) minimising issued MMA rows.
