@@ -350,10 +350,13 @@ __global__ void wgrad_umma_reduce_kernel(const float* __restrict__ ws, int split
 }
 
 // ------------------------------------------------------------------ host side
-// N = 128 variant: measured on B200 slightly SLOWER than N = 64 with two tap groups (0.422 vs 0.407 ms on 256->256 @100^2,
-// 1.30 vs 1.16 ms on 1024->512 @54^2): the kernel is fed from L2, not MMA-rate-bound, and three passes need smaller
-// tiles.  Kept for experiments: B200UNET_WGRAD_N128=1 enables it.
-static int g_wgrad_n128 = getenv("B200UNET_WGRAD_N128") ? 1 : 0;
+// N = 128 variant and pipeline depth, measured on B200 at batch 32 (ms: 256->256 @136^2 / 128->128 @280^2 / 1024->512 @54^2):
+//   N = 64,  >= 3 stages : 0.705 / 0.885 / 1.156      N = 128, >= 3 stages : 0.767 / 0.895 / 1.297
+//   N = 64,  >= 2 stages : 0.702 / 0.863 / 1.033      N = 128, >= 2 stages : 0.688 / 0.843 / 0.898   <- default
+// (three passes need big K tiles to pay off, and big tiles only fit twice into shared memory).
+// B200UNET_WGRAD_N64=1 / B200UNET_WGRAD_MIN_STAGES=k override for experiments.
+static int g_wgrad_n128 = getenv("B200UNET_WGRAD_N64") ? 0 : 1;
+static int g_wgrad_min_stages = getenv("B200UNET_WGRAD_MIN_STAGES") ? atoi(getenv("B200UNET_WGRAD_MIN_STAGES")) : 2;
 
 struct WgPlan {
   WgArgs a;
@@ -427,7 +430,7 @@ static bool wg_make_plan(int mode, int Ho, int Wo, int n_img, int m_total, int n
       const uint32_t g_rows = (uint32_t)max((TH + a.halo) * P, kt + a.halo * P + a.halo);
       const uint32_t g_tile = (g_rows * 128 + 1023) & ~1023u;
       const uint32_t stage = 2 * r_blk + g_tiles * g_tile;
-      if (3 * stage + kWgOnesBytes + 1024 > kWgSmemBudget) continue;  // >= 3 stages: fed from L2, latency must hide
+      if ((uint32_t)g_wgrad_min_stages * stage + kWgOnesBytes + 1024 > kWgSmemBudget) continue;  // >= 3 stages: fed from L2, latency must hide
       const long long tiles = (long long)((Wo + TW - 1) / TW) * ((Ho + TH - 1) / TH) * n_img;
       // per tile and pass: MMA time ~ MMA groups * K steps * ~48 cycles (shared-memory-bound N = 64 MMA), load time ~
       // bytes moved L2 -> SMEM at ~32 B/cycle/SM; whichever is larger, plus a fixed per-tile cost
