@@ -1,0 +1,42 @@
+"""Whole training step (forward, fused loss, backward, optimizer) captured in ONE CUDA graph.
+
+Every kernel of libb200unet.so launches on the stream it is given, never synchronises and never allocates, so a
+training step is capturable as is.  For small / narrow configurations (e.g. the repo's feature net, 3x192x640) the
+eager step is bound by Python launch overhead; one `cudaGraphLaunch` removes it.
+
+    step = GraphedTrainStep(model, torch.optim.Adam(model.parameters(), capturable=True, fused=True), x, y)
+    loss = step(x_new, y_new)        # copies into the static inputs, replays, returns the (static) loss tensor
+"""
+from __future__ import annotations
+
+import torch
+
+
+class GraphedTrainStep:
+    def __init__(self, model, optimizer, x: torch.Tensor, y: torch.Tensor, warmup: int = 3):
+        self.model, self.opt = model, optimizer
+        self.x, self.y = x.clone(), y.clone()
+        # warm-up on a side stream: autograd nodes born on the legacy default stream would invalidate the capture
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._step()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._step()
+
+    def _step(self) -> torch.Tensor:
+        loss = self.model.loss(self.x, self.y)
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        self.opt.step()
+        return loss.detach()
+
+    def __call__(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        self.x.copy_(x, non_blocking=True)
+        self.y.copy_(y, non_blocking=True)
+        self.graph.replay()
+        return self.loss

@@ -195,3 +195,47 @@ def test_two_forwards_then_backward():
     got = torch.cat([g[k].flatten() for k in leaves])
     want = torch.cat([leaves[k].grad.flatten() for k in leaves])
     assert rel_l2(got, want) < TOL_GRAD
+
+
+def test_cuda_graph_step_matches_eager():
+    """The whole training step is CUDA-graph capturable (no allocation / sync inside the library) and replays to the
+    same weights as the eager step."""
+    import b200unet
+    spec = O.UNetSpec(3, 4, 3, 2, True, True, "upsample", True, "deep")   # narrow + BN + padded channels: most host logic
+    sd = O.init_params(spec, seed=2)
+    g = torch.Generator().manual_seed(3)
+    xs = [torch.randn(2, 3, 40, 48, generator=g).cuda() for _ in range(3)]
+    ys = [torch.randint(0, 4, (2, 40, 48), generator=g).cuda() for _ in range(3)]
+
+    def fresh():
+        m = build(spec.__dict__).cuda().train()
+        m.load_state_dict(sd)
+        return m, torch.optim.Adam(m.parameters(), lr=1e-3, capturable=True, fused=True)
+
+    m1, o1 = fresh()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        eager_losses = []
+        for x, y in zip(xs, ys):
+            loss = m1.loss(x, y)
+            o1.zero_grad(set_to_none=True)
+            loss.backward()
+            o1.step()
+            eager_losses.append(float(loss.detach()))
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    m2, o2 = fresh()
+    step = b200unet.GraphedTrainStep(m2, o2, xs[0], ys[0])   # warms up (optimizer state must exist before capture)
+    m2.load_state_dict(sd)                                   # rewind the warm-up updates: weights, BN buffers ...
+    for st in o2.state.values():                             # ... and Adam moments / step counters (in place)
+        for v in st.values():
+            if torch.is_tensor(v):
+                v.zero_()
+    graph_losses = [float(step(x, y)) for x, y in zip(xs, ys)]
+    assert graph_losses[0] == eager_losses[0]
+    for a, b in zip(graph_losses, eager_losses):
+        assert abs(a - b) <= 2e-3 * max(1.0, abs(b))
+    w1 = torch.cat([p.detach().flatten() for p in m1.parameters()])
+    w2 = torch.cat([p.detach().flatten() for p in m2.parameters()])
+    assert rel_l2(w2.cpu(), w1.cpu()) < 1e-3
