@@ -62,16 +62,17 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadArgs a) {
   float gs = 1.f;
   if (MODE == HEAD_CE_BWD) gs = (a.gscale ? a.gscale[0] : 1.f) * a.ce_state[1];
 
-  for (long long p0 = (long long)blockIdx.x * slots; p0 < npix; p0 += (long long)gridDim.x * slots) {
-    const long long p = p0 + slot;
-    const bool live = p < npix;
-    int n = 0, ih = 0, iw = 0;
-    if (live) {
-      n = (int)(p / hw);
-      const long long r = p - n * hw;
-      ih = (int)(r / a.x.w);
-      iw = (int)(r - (long long)ih * a.x.w);
-    }
+  // work unit = `slots` consecutive pixels of one image row: only 32-bit index arithmetic per iteration (the 64-bit
+  // divisions of a flat pixel index sat in front of every load)
+  const unsigned upr = (unsigned)(a.x.w + slots - 1) / slots;       // units per row
+  const unsigned units = (unsigned)a.x.n * a.x.h * upr;
+  (void)npix;
+  for (unsigned u = blockIdx.x; u < units; u += gridDim.x) {
+    const unsigned row = u / upr, cb = u - row * upr;
+    const int n = (int)(row / a.x.h), ih = (int)(row - (unsigned)n * a.x.h);
+    const int iw = (int)(cb * slots) + slot;
+    const bool live = iw < a.x.w;
+    const long long p = (long long)row * a.x.w + iw;
     const bf16* xp = a.x.p + a.x.off(n, ih, iw);
     float z[KMAX];
 #pragma unroll

@@ -18,15 +18,11 @@ __device__ __forceinline__ void pool_scan(float v, int code, float& best, int& a
 template <int VEC>
 __global__ void __launch_bounds__(256)
 maxpool_fwd_kernel(DView x, DView y, uint8_t* __restrict__ idx8, long long* __restrict__ idx64) {
+  // one block per output row (n, oh): only 32-bit index arithmetic per element
   const int lanes = y.c / VEC;
-  const long long total = (long long)y.n * y.h * y.w * lanes;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int l = (int)(e % lanes);
-    long long p = e / lanes;
-    const int ow = (int)(p % y.w);
-    p /= y.w;
-    const int oh = (int)(p % y.h);
-    const int n = (int)(p / y.h);
+  const int n = blockIdx.x / y.h, oh = blockIdx.x - n * y.h;
+  for (int e = threadIdx.x; e < y.w * lanes; e += blockDim.x) {
+    const int ow = e / lanes, l = e - ow * lanes;
     float v[4][VEC];
 #pragma unroll
     for (int a = 0; a < 2; ++a)
@@ -80,16 +76,12 @@ template <int VEC>
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(DView dy, const uint8_t* __restrict__ idx8, DView dx, DView add, int has_add, int add_y, int add_x,
                    const bf16* __restrict__ mask) {
+  // one block per window row (n, oh): only 32-bit index arithmetic per element
   const int lanes = dx.c / VEC;
   const int wh = (dx.h + 1) / 2, ww = (dx.w + 1) / 2;
-  const long long total = (long long)dx.n * wh * ww * lanes;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int l = (int)(e % lanes);
-    long long p = e / lanes;
-    const int ow = (int)(p % ww);
-    p /= ww;
-    const int oh = (int)(p % wh);
-    const int n = (int)(p / wh);
+  const int n = blockIdx.x / wh, oh = blockIdx.x - n * wh;
+  for (int e = threadIdx.x; e < ww * lanes; e += blockDim.x) {
+    const int ow = e / lanes, l = e - ow * lanes;
     const bool win = oh < dy.h && ow < dy.w;
     float g[VEC];
     int code[VEC];
@@ -170,12 +162,11 @@ int b200unet_maxpool2x2_fwd(const b200_view* x, const b200_view* y, uint8_t* idx
   B200_REQUIRE(y->n == x->n && y->c == x->c && y->h == x->h / 2 && y->w == x->w / 2,
                "maxpool_fwd: output extent must be floor(input/2)");
   const bool v8 = vec8_ok(*x) && vec8_ok(*y) && reinterpret_cast<uintptr_t>(idx8) % 8 == 0;
-  const long long total = view_pixels(*y) * (v8 ? y->c / 8 : y->c);
   if (v8)
-    maxpool_fwd_kernel<8><<<stream_grid(total), 256, 0, as_stream(stream)>>>(dview(*x), dview(*y), idx8,
+    maxpool_fwd_kernel<8><<<(unsigned)(y->n * y->h), 256, 0, as_stream(stream)>>>(dview(*x), dview(*y), idx8,
                                                                             (long long*)idx64);
   else
-    maxpool_fwd_kernel<1><<<stream_grid(total), 256, 0, as_stream(stream)>>>(dview(*x), dview(*y), idx8,
+    maxpool_fwd_kernel<1><<<(unsigned)(y->n * y->h), 256, 0, as_stream(stream)>>>(dview(*x), dview(*y), idx8,
                                                                             (long long*)idx64);
   return check_launch("maxpool_fwd");
 }
@@ -192,13 +183,12 @@ int b200unet_maxpool2x2_bwd(const b200_view* dy, const uint8_t* idx8, const b200
   }
   const bool v8 = vec8_ok(*dy) && vec8_ok(*dx) && (!add || vec8_ok(*add)) &&
                   reinterpret_cast<uintptr_t>(idx8) % 8 == 0 && reinterpret_cast<uintptr_t>(mask) % 16 == 0;
-  const long long total = (long long)dx->n * ((dx->h + 1) / 2) * ((dx->w + 1) / 2) * (v8 ? dx->c / 8 : dx->c);
   DView dadd = add ? dview(*add) : dview(*dx);
   if (v8)
-    maxpool_bwd_kernel<8><<<stream_grid(total), 256, 0, as_stream(stream)>>>(dview(*dy), idx8, dview(*dx), dadd,
+    maxpool_bwd_kernel<8><<<(unsigned)(dx->n * ((dx->h + 1) / 2)), 256, 0, as_stream(stream)>>>(dview(*dy), idx8, dview(*dx), dadd,
                                                                             add ? 1 : 0, add_y, add_x, (const bf16*)mask);
   else
-    maxpool_bwd_kernel<1><<<stream_grid(total), 256, 0, as_stream(stream)>>>(dview(*dy), idx8, dview(*dx), dadd,
+    maxpool_bwd_kernel<1><<<(unsigned)(dx->n * ((dx->h + 1) / 2)), 256, 0, as_stream(stream)>>>(dview(*dy), idx8, dview(*dx), dadd,
                                                                             add ? 1 : 0, add_y, add_x, (const bf16*)mask);
   return check_launch("maxpool_bwd");
 }
