@@ -35,13 +35,11 @@ __global__ void bn_finalize_stats_kernel(const float* __restrict__ partial, int 
                                          float momentum, float* __restrict__ running_mean,
                                          float* __restrict__ running_var, float* __restrict__ save_mean,
                                          float* __restrict__ save_invstd) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // one warp per channel
   if (ch >= c) return;
-  double s = 0.0, ss = 0.0;
-  for (int b = 0; b < blocks; ++b) {
-    s += (double)partial[((long long)b * 2 + 0) * c + ch];
-    ss += (double)partial[((long long)b * 2 + 1) * c + ch];
-  }
+  const double s = warp_partial_sum(partial, blocks, 2LL * c, ch);
+  const double ss = warp_partial_sum(partial, blocks, 2LL * c, (long long)c + ch);
+  if ((threadIdx.x & 31) != 0) return;
   const double mean = s / count;
   double var = ss / count - mean * mean;  // biased
   if (var < 0.0) var = 0.0;
@@ -56,13 +54,11 @@ __global__ void bn_finalize_stats_kernel(const float* __restrict__ partial, int 
 
 __global__ void bn_finalize_bwd_kernel(const float* __restrict__ partial, int blocks, int c, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, float* __restrict__ sums /* [2][c] */) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // one warp per channel
   if (ch >= c) return;
-  double s = 0.0, ss = 0.0;
-  for (int b = 0; b < blocks; ++b) {
-    s += (double)partial[((long long)b * 2 + 0) * c + ch];
-    ss += (double)partial[((long long)b * 2 + 1) * c + ch];
-  }
+  const double s = warp_partial_sum(partial, blocks, 2LL * c, ch);
+  const double ss = warp_partial_sum(partial, blocks, 2LL * c, (long long)c + ch);
+  if ((threadIdx.x & 31) != 0) return;
   dbeta[ch] = (float)s;
   dgamma[ch] = (float)ss;
   sums[ch] = (float)s;
@@ -178,7 +174,7 @@ int b200unet_bn_fwd_train(const b200_view* x, const b200_view* y, const float* g
   ReducePlan pl;
   int r = launch_chan_reduce<2, false>(StatsF(), *x, nullptr, (float*)workspace, &pl, st);
   if (r) return r;
-  bn_finalize_stats_kernel<<<(x->c + 127) / 128, 128, 0, st>>>((const float*)workspace, pl.blocks, x->c,
+  bn_finalize_stats_kernel<<<finalize_grid(x->c), kFinalizeThreads, 0, st>>>((const float*)workspace, pl.blocks, x->c,
                                                               (double)view_pixels(*x), eps, momentum, running_mean,
                                                               running_var, save_mean, save_invstd);
   r = check_launch("bn finalize");
@@ -222,7 +218,7 @@ int b200unet_bn_bwd(const b200_view* x, const b200_view* dy, const b200_view* dx
   BwdSumsF f{save_mean, save_invstd};
   int r = launch_chan_reduce<2, true>(f, *x, dy, partial, &pl, st);
   if (r) return r;
-  bn_finalize_bwd_kernel<<<(x->c + 127) / 128, 128, 0, st>>>(partial, pl.blocks, x->c, dgamma, dbeta, sums);
+  bn_finalize_bwd_kernel<<<finalize_grid(x->c), kFinalizeThreads, 0, st>>>(partial, pl.blocks, x->c, dgamma, dbeta, sums);
   r = check_launch("bn bwd finalize");
   if (r) return r;
   const bool v8 = vec8_ok(*x) && vec8_ok(*dy) && vec8_ok(*dx);

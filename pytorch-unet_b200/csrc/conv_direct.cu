@@ -231,18 +231,17 @@ struct SumF2 {
   }
 };
 __global__ void finalize_sum2_kernel(const float* __restrict__ partial, int blocks, int c, float* __restrict__ out) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (ch >= c) return;
-  double s = 0.0;
-  for (int b = 0; b < blocks; ++b) s += (double)partial[(long long)b * c + ch];
-  out[ch] = (float)s;
+  const double s = warp_partial_sum(partial, blocks, c, ch);
+  if ((threadIdx.x & 31) == 0) out[ch] = (float)s;
 }
 
 int bias_grad(const b200_view& dz, float* db, void* ws, cudaStream_t st) {
   ReducePlan pl;
   int r = launch_chan_reduce<1, false>(SumF2(), dz, nullptr, (float*)ws, &pl, st);
   if (r) return r;
-  finalize_sum2_kernel<<<(dz.c + 127) / 128, 128, 0, st>>>((const float*)ws, pl.blocks, dz.c, db);
+  finalize_sum2_kernel<<<finalize_grid(dz.c), kFinalizeThreads, 0, st>>>((const float*)ws, pl.blocks, dz.c, db);
   return check_launch("bias_grad");
 }
 

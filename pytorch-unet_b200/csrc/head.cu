@@ -5,7 +5,7 @@
 // Thread mapping: 8 lanes cooperate on one pixel, each lane owns one 16-byte vector of every 64-channel chunk,
 // so a warp reads 4 pixels x 128 contiguous bytes per instruction.  blockIdx.y selects the 64-channel chunk whose
 // dx / dW this block produces (the dot product itself always runs over all channels).
-#include "common.cuh"
+#include "chan_reduce.cuh"
 
 namespace b200 {
 
@@ -264,12 +264,10 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadArgs a) {
 
 __global__ void head_ce_finalize_kernel(const float* __restrict__ ws, int blocks, float* __restrict__ loss,
                                         float* __restrict__ ce_state) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double l = 0.0, cn = 0.0;
-  for (int b = 0; b < blocks; ++b) {
-    l += (double)ws[b * 2];
-    cn += (double)ws[b * 2 + 1];
-  }
+  if (threadIdx.x >= 32 || blockIdx.x != 0) return;
+  const double l = warp_partial_sum(ws, blocks, 2, 0);
+  const double cn = warp_partial_sum(ws, blocks, 2, 1);
+  if (threadIdx.x != 0) return;
   const float v = (float)(l / cn);  // 0/0 = NaN when every label is ignored, like F.cross_entropy
   if (loss) loss[0] = v;
   ce_state[0] = v;
@@ -278,10 +276,10 @@ __global__ void head_ce_finalize_kernel(const float* __restrict__ ws, int blocks
 
 __global__ void head_bwd_finalize_kernel(const float* __restrict__ ws, int blocks, int kc, int k, float* __restrict__ dw,
                                          float* __restrict__ db) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // one warp per output
   if (q >= kc + k) return;
-  double s = 0.0;
-  for (int b = 0; b < blocks; ++b) s += (double)ws[(long long)b * (kc + k) + q];
+  const double s = warp_partial_sum(ws, blocks, kc + k, q);
+  if ((threadIdx.x & 31) != 0) return;
   if (q < kc)
     dw[q] = (float)s;
   else if (db)
@@ -367,7 +365,7 @@ int b200unet_head_bwd(const b200_view* x, const float* w, const float* b, int n_
   int r = launch_head<HEAD_BWD>(a, blocks, as_stream(stream));
   if (r) return r;
   const int kc = n_classes * x->c;
-  head_bwd_finalize_kernel<<<(kc + n_classes + 127) / 128, 128, 0, as_stream(stream)>>>((const float*)workspace, blocks,
+  head_bwd_finalize_kernel<<<finalize_grid(kc + n_classes), kFinalizeThreads, 0, as_stream(stream)>>>((const float*)workspace, blocks,
                                                                                         kc, n_classes, dw, db);
   return check_launch("head_bwd finalize");
 }
@@ -417,7 +415,7 @@ int b200unet_head_ce_bwd(const b200_view* x, const float* w, const float* b, int
   int r = launch_head<HEAD_CE_BWD>(a, blocks, as_stream(stream));
   if (r) return r;
   const int kc = n_classes * x->c;
-  head_bwd_finalize_kernel<<<(kc + n_classes + 127) / 128, 128, 0, as_stream(stream)>>>((const float*)workspace, blocks,
+  head_bwd_finalize_kernel<<<finalize_grid(kc + n_classes), kFinalizeThreads, 0, as_stream(stream)>>>((const float*)workspace, blocks,
                                                                                         kc, n_classes, dw, db);
   return check_launch("head_ce_bwd finalize");
 }

@@ -158,11 +158,10 @@ struct SumF {
 };
 
 __global__ void finalize_sum_kernel(const float* __restrict__ partial, int blocks, int c, float* __restrict__ out) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (ch >= c) return;
-  double s = 0.0;
-  for (int b = 0; b < blocks; ++b) s += (double)partial[(long long)b * c + ch];
-  out[ch] = (float)s;
+  const double s = warp_partial_sum(partial, blocks, c, ch);
+  if ((threadIdx.x & 31) == 0) out[ch] = (float)s;
 }
 
 inline int grid_for(long long total, int threads) {
@@ -262,7 +261,7 @@ int b200unet_channel_sum(const b200_view* dz, float* out, void* workspace, size_
   ReducePlan pl;
   int r = launch_chan_reduce<1, false>(SumF(), *dz, nullptr, (float*)workspace, &pl, as_stream(stream));
   if (r) return r;
-  finalize_sum_kernel<<<(dz->c + 127) / 128, 128, 0, as_stream(stream)>>>((const float*)workspace, pl.blocks, dz->c, out);
+  finalize_sum_kernel<<<finalize_grid(dz->c), kFinalizeThreads, 0, as_stream(stream)>>>((const float*)workspace, pl.blocks, dz->c, out);
   return check_launch("channel_sum finalize");
 }
 }
