@@ -14,9 +14,14 @@ CFG = {
     "config4 d4 wf5 in3 same 3x1024x1024 b8": ((3, 2, 4, 5, True, False, "upconv"), "paper", 8, 1024, 1024),
     "config5 deep feature variant 3x192x640 b12": ((3, 6, 5, 2, True, True, "upsample", True), "deep", 12, 192, 640),
 }
-for name, (args, ub, b, h, w) in CFG.items():
+RUNS = []
+for name, cfg in CFG.items():
+    RUNS.append((name, cfg, "auto"))
+    if cfg[0][5]:  # BatchNorm graphs: auto = split tier; also time the plain bf16 tier
+        RUNS.append((name + " [precision=bf16]", cfg, "bf16"))
+for name, (args, ub, b, h, w), tier in RUNS:
     torch.manual_seed(0)
-    m = b200unet.UNet(*args, up_block=ub).cuda().train()
+    m = b200unet.UNet(*args, up_block=ub, precision=tier).cuda().train()
     opt = torch.optim.Adam(m.parameters(), lr=1e-4, fused=True)
     spec = O.UNetSpec(*args[:7], non_neg=(args[7] if len(args) > 7 else False), up_block=ub)
     ho, wo = O.output_hw(spec, h, w)
@@ -31,4 +36,4 @@ for name, (args, ub, b, h, w) in CFG.items():
     for _ in range(10): step()
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
-    print(f"{name:48s} {ms:8.2f} ms/step  {b / ms * 1e3:9.1f} img/s  (host wall {1e2 * (time.perf_counter() - t0):.2f} ms/step)", flush=True)
+    print(f"{name:64s} {m.precision:5s} {ms:8.2f} ms/step  {b / ms * 1e3:9.1f} img/s  (host wall {1e2 * (time.perf_counter() - t0):.2f} ms/step)", flush=True)

@@ -38,11 +38,21 @@
 extern "C" {
 #endif
 
-#define B200UNET_ABI_VERSION 2
+#define B200UNET_ABI_VERSION 3
 
-/* Strided NHWC view of a bf16 tensor.  Channel stride is 1.  Strides in elements. */
+/* Strided NHWC view of a bf16 tensor.  Channel stride is 1.  Strides in elements.
+ *
+ * Precision tiers.  bf16 tier: lo == NULL, the tensor is the bf16 plane at ptr.  Split tier (BatchNorm graphs, whose
+ * forward error in plain bf16 exceeds the parity tolerance — DESIGN.md section 4): the value is carried as TWO bf16
+ * planes of identical geometry, value = *ptr + *lo (~16 mantissa bits).  The FORWARD entry points (conv_fwd,
+ * convt_fwd, bn_fwd_*, maxpool2x2_fwd, bilinear_up2x_fwd, head_fwd, head_ce_fwd, nchw_f32_to_nhwc_bf16) read
+ * hi + lo from input views that carry a lo plane and write both planes of output views that carry one; conv weights
+ * for them are packed with the *_SPLIT pack modes (three operand passes: hi*hi + lo*hi + hi*lo, fp32 accumulate).
+ * Every BACKWARD entry point reads the hi plane only and ignores lo: measured on the oracle, gradient accuracy is
+ * set by the forward activations, not by the operand precision of the backward GEMMs.                          */
 typedef struct {
   void* ptr;
+  void* lo; /* NULL, or the low-order plane (same extents and strides as ptr) */
   int32_t n, h, w, c;
   int64_t stride_n, stride_h, stride_w;
 } b200_view;
@@ -54,7 +64,9 @@ enum { B200_IMPL_AUTO = 0, B200_IMPL_DIRECT = 1, B200_IMPL_UMMA = 2 };
 /* ---- conv (3x3 or 1x1), forward.  y = act(conv(cat(src[0], src[1]), W) + b)
  * src[i]: the (already center-cropped) input windows, all of extent n x (h_out + (k-1) - 2 pad) x (w_out + ...).
  * Reads outside a window are zero (that is the zero padding of nn.Conv2d applied to the cropped tensor).
- * w_packed: bf16 [cout][taps][kpad], kpad = sum_i roundup(src[i].c, 64)   (pack_conv_weight, mode 0)      */
+ * w_packed: bf16 [cout][taps][kpad], kpad = sum_i roundup(src[i].c, 64)   (pack_conv_weight, mode 0);
+ *           split tier (any src[i].lo != NULL; then all sources and dst must carry lo planes, tcgen05 path only):
+ *           [cout][taps][3*kpad] = {hi(W) | hi(W) | lo(W)} multiplying {hi(x) | lo(x) | hi(x)}  (mode 2)        */
 typedef struct {
   b200_view src[2];
   int32_t num_src;
@@ -99,7 +111,8 @@ typedef struct {
 } b200_conv_wgrad_params;
 
 /* ---- ConvTranspose2d(k=2, s=2).  y[n, 2i+a, 2j+b, o] = bias[o] + sum_c x[n,i,j,c] * W[c,o,a,b]
- * w_packed (fwd):  bf16 [(a*2+b)*cout + o][roundup(cin,64)]   (pack_convt_weight mode 0)
+ * w_packed (fwd):  bf16 [(a*2+b)*cout + o][roundup(cin,64)]   (pack_convt_weight mode 0; split tier: mode 2,
+ *                  [..][3*roundup(cin,64)] laid out like the conv's)
  * w_packed (dgrad): bf16 [cin][a*2+b][roundup(cout,64)]       (pack_convt_weight mode 1)                   */
 typedef struct {
   b200_view x;  /* n,h,w,cin */
@@ -157,9 +170,11 @@ int b200unet_convt_wgrad_impl(const b200_convt_wgrad_params* p);
  * conv: w [cout][cin_total][k][k]; src_c[i] = channels of source i (cin_total = sum).
  *   mode 0 (fprop): out [cout][taps][kpad],             kpad = sum roundup(src_c[i], 64)
  *   mode 1 (dgrad): out [cin_total][taps][roundup(cout,64)], taps spatially flipped
+ *   mode 2 (fprop, split tier): out [cout][taps][3*kpad] = {hi(w) | hi(w) | lo(w)}, hi = bf16(w), lo = bf16(w - hi)
  * convt: w [cin][cout][2][2]
  *   mode 0 (fwd):   out [(a*2+b)*cout + o][roundup(cin,64)]
- *   mode 1 (dgrad): out [cin][a*2+b][roundup(cout,64)]                                                     */
+ *   mode 1 (dgrad): out [cin][a*2+b][roundup(cout,64)]
+ *   mode 2 (fwd, split tier): out [(a*2+b)*cout + o][3*roundup(cin,64)] = {hi | hi | lo}                    */
 size_t b200unet_pack_conv_weight_bytes(int cout, int num_src, const int* src_c, int taps, int mode);
 int b200unet_pack_conv_weight(const float* w, int cout, int num_src, const int* src_c, int taps, int mode,
                               void* out, void* stream);

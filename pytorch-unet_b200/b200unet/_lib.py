@@ -17,9 +17,9 @@ IMPL_AUTO, IMPL_DIRECT, IMPL_UMMA = 0, 1, 2
 
 
 class View(C.Structure):
-    """b200_view: strided NHWC bf16 window."""
+    """b200_view: strided NHWC bf16 window (+ optional low-order plane of the split precision tier)."""
 
-    _fields_ = [("ptr", C.c_void_p), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32),
+    _fields_ = [("ptr", C.c_void_p), ("lo", C.c_void_p), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32),
                 ("stride_n", C.c_int64), ("stride_h", C.c_int64), ("stride_w", C.c_int64)]
 
 
@@ -122,7 +122,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.b200unet_abi_version() != 2:
+    if lib.b200unet_abi_version() != 3:
         raise RuntimeError("libb200unet.so ABI version mismatch: rebuild with pytorch-unet_b200/build.py")
     _lib = lib
     return lib
@@ -134,11 +134,51 @@ def check(rc: int, what: str) -> None:
         raise RuntimeError(f"b200unet {what} failed (rc={rc}): {msg}")
 
 
-def view(t: torch.Tensor) -> View:
-    """b200_view of an NHWC bf16 tensor (any strides with unit channel stride)."""
+class Split:
+    """Activation of the split precision tier: value = hi + lo, two NHWC bf16 tensors of identical geometry
+    (include/b200unet.h).  Forward operators accept and return it in place of a plain tensor; backward operators take
+    `.hi` only."""
+
+    __slots__ = ("hi", "lo")
+
+    def __init__(self, hi: torch.Tensor, lo: torch.Tensor):
+        assert hi.shape == lo.shape and hi.stride() == lo.stride() and hi.dtype == lo.dtype == torch.bfloat16
+        self.hi, self.lo = hi, lo
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+    @property
+    def device(self):
+        return self.hi.device
+
+    def __getitem__(self, idx) -> "Split":  # windows (center crop) apply to both planes
+        return Split(self.hi[idx], self.lo[idx])
+
+    def float(self) -> torch.Tensor:
+        return self.hi.float() + self.lo.float()
+
+    @staticmethod
+    def from_float(x: torch.Tensor) -> "Split":
+        hi = x.to(torch.bfloat16)
+        return Split(hi, (x - hi.float()).to(torch.bfloat16))
+
+
+def hi_of(t):
+    """The bf16 plane backward operators read."""
+    return t.hi if isinstance(t, Split) else t
+
+
+def view(t) -> View:
+    """b200_view of an NHWC bf16 tensor (any strides with unit channel stride) or of a Split pair."""
+    lo = None
+    if isinstance(t, Split):
+        t, lo = t.hi, t.lo
     assert t.dim() == 4 and t.dtype == torch.bfloat16, (t.shape, t.dtype)
     assert t.stride(3) == 1 or t.shape[3] == 1
-    return View(t.data_ptr(), t.shape[0], t.shape[1], t.shape[2], t.shape[3], t.stride(0), t.stride(1), t.stride(2))
+    return View(t.data_ptr(), None if lo is None else lo.data_ptr(), t.shape[0], t.shape[1], t.shape[2], t.shape[3],
+                t.stride(0), t.stride(1), t.stride(2))
 
 
 def ptr(t):

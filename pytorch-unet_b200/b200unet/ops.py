@@ -12,9 +12,9 @@ import torch
 
 from . import _lib
 from ._lib import (IMPL_AUTO, IMPL_DIRECT, IMPL_UMMA, ConvDgradParams, ConvFwdParams, ConvTDgradParams,
-                   ConvTFwdParams, ConvTWgradParams, ConvWgradParams, check, ptr, stream_ptr, view)
+                   ConvTFwdParams, ConvTWgradParams, ConvWgradParams, Split, check, hi_of, ptr, stream_ptr, view)
 
-__all__ = ["IMPL_AUTO", "IMPL_DIRECT", "IMPL_UMMA"]
+__all__ = ["IMPL_AUTO", "IMPL_DIRECT", "IMPL_UMMA", "Split", "hi_of"]
 
 _workspaces = {}
 
@@ -34,17 +34,19 @@ def tensor_cores_available() -> bool:
     return bool(_lib.load().b200unet_device_ok())
 
 
-def _nhwc_empty(n, h, w, c, device) -> torch.Tensor:
-    return torch.empty((n, h, w, c), dtype=torch.bfloat16, device=device)
+def _nhwc_empty(n, h, w, c, device, split: bool = False):
+    """Output activation: a bf16 tensor, or a hi/lo pair in the split precision tier."""
+    hi = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=device)
+    return Split(hi, torch.empty_like(hi)) if split else hi
 
 
 # ------------------------------------------------------------------ layout
-def to_nhwc(x: torch.Tensor) -> torch.Tensor:
-    """fp32 NCHW (module input, unet.py:73) -> bf16 NHWC."""
+def to_nhwc(x: torch.Tensor, split: bool = False):
+    """fp32 NCHW (module input, unet.py:73) -> bf16 NHWC (hi/lo pair in the split tier)."""
     assert x.dim() == 4 and x.dtype == torch.float32 and x.is_cuda
     x = x.contiguous()
     n, c, h, w = x.shape
-    y = _nhwc_empty(n, h, w, c, x.device)
+    y = _nhwc_empty(n, h, w, c, x.device, split)
     v = view(y)
     check(_lib.load().b200unet_nchw_f32_to_nhwc_bf16(x.data_ptr(), C.byref(v), stream_ptr()), "nchw_f32_to_nhwc_bf16")
     return y
@@ -69,7 +71,7 @@ def im2col3x3(x: torch.Tensor, pad: int) -> torch.Tensor:
 
 
 def pack_conv_weight(w: torch.Tensor, src_c: Sequence[int], mode: int) -> torch.Tensor:
-    """fp32 [cout][cin][k][k] -> bf16 GEMM operand (mode 0: fprop, 1: dgrad)."""
+    """fp32 [cout][cin][k][k] -> bf16 GEMM operand (mode 0: fprop, 1: dgrad, 2: fprop of the split tier)."""
     lib = _lib.load()
     cout, cin, k, _ = w.shape
     assert sum(src_c) == cin and w.dtype == torch.float32 and w.is_contiguous()
@@ -101,8 +103,9 @@ def conv_fwd(srcs: Sequence[torch.Tensor], w: torch.Tensor, bias: Optional[torch
     cout, cin, k, _ = w.shape
     n, h, wd, _ = srcs[0].shape
     ho, wo = h + 2 * pad - (k - 1), wd + 2 * pad - (k - 1)
+    split = isinstance(srcs[0], Split)
     if out is None:
-        out = _nhwc_empty(n, ho, wo, cout, srcs[0].device)
+        out = _nhwc_empty(n, ho, wo, cout, srcs[0].device, split)
     p = ConvFwdParams()
     for i, s in enumerate(srcs):
         p.src[i] = view(s)
@@ -111,7 +114,7 @@ def conv_fwd(srcs: Sequence[torch.Tensor], w: torch.Tensor, bias: Optional[torch
     p.dst, p.impl = view(out), impl
     if impl != IMPL_DIRECT and lib.b200unet_conv_fwd_impl(C.byref(p)) == IMPL_UMMA:
         if w_packed is None:
-            w_packed = pack_conv_weight(w, [s.shape[3] for s in srcs], 0)
+            w_packed = pack_conv_weight(w, [s.shape[3] for s in srcs], 2 if split else 0)
         p.w_packed = w_packed.data_ptr()
     check(lib.b200unet_conv_fwd(C.byref(p), stream_ptr()), "conv_fwd")
     return out
@@ -168,14 +171,15 @@ def convt_fwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], w_
     lib = _lib.load()
     n, h, wd, cin = x.shape
     cout = w.shape[1]
+    split = isinstance(x, Split)
     if out is None:
-        out = _nhwc_empty(n, 2 * h, 2 * wd, cout, x.device)
+        out = _nhwc_empty(n, 2 * h, 2 * wd, cout, x.device, split)
     p = ConvTFwdParams()
     p.x, p.y = view(x), view(out)
     p.w_f32, p.bias, p.impl = w.data_ptr(), ptr(bias), impl
     if impl != IMPL_DIRECT and lib.b200unet_convt_fwd_impl(C.byref(p)) == IMPL_UMMA:
         if w_packed is None:
-            w_packed = pack_convt_weight(w, 0)
+            w_packed = pack_convt_weight(w, 2 if split else 0)
         p.w_packed = w_packed.data_ptr()
     check(lib.b200unet_convt_fwd(C.byref(p), stream_ptr()), "convt_fwd")
     return out
@@ -215,7 +219,7 @@ def convt_wgrad(x: torch.Tensor, dy: torch.Tensor, want_db: bool = True, impl: i
 def maxpool_fwd(x: torch.Tensor, want_idx64: bool = False):
     """F.max_pool2d(x, 2): returns (y, idx8[, idx64]); idx8 = a*2+b code of the arg-max inside the window."""
     n, h, w, c = x.shape
-    y = _nhwc_empty(n, h // 2, w // 2, c, x.device)
+    y = _nhwc_empty(n, h // 2, w // 2, c, x.device, isinstance(x, Split))
     idx8 = torch.empty((n, h // 2, w // 2, c), dtype=torch.uint8, device=x.device)
     idx64 = torch.empty((n, h // 2, w // 2, c), dtype=torch.int64, device=x.device) if want_idx64 else None
     vx, vy = view(x), view(y)
@@ -235,9 +239,9 @@ def maxpool_bwd(dy: torch.Tensor, idx8: torch.Tensor, dx: torch.Tensor, add: Opt
                                               stream_ptr()), "maxpool2x2_bwd")
 
 
-def bilinear_fwd(x: torch.Tensor) -> torch.Tensor:
+def bilinear_fwd(x):
     n, h, w, c = x.shape
-    y = _nhwc_empty(n, 2 * h, 2 * w, c, x.device)
+    y = _nhwc_empty(n, 2 * h, 2 * w, c, x.device, isinstance(x, Split))
     vx, vy = view(x), view(y)
     check(_lib.load().b200unet_bilinear_up2x_fwd(C.byref(vx), C.byref(vy), stream_ptr()), "bilinear_up2x_fwd")
     return y
@@ -252,8 +256,8 @@ def bilinear_bwd(dy: torch.Tensor, dx: torch.Tensor, mask: Optional[torch.Tensor
 # ------------------------------------------------------------------ batch norm
 def bn_fwd_train(x, gamma, beta, running_mean, running_var, momentum: float, eps: float):
     lib = _lib.load()
-    c = x.shape[3]
-    y = torch.empty_like(x)
+    n, h, w, c = x.shape
+    y = _nhwc_empty(n, h, w, c, x.device, isinstance(x, Split))
     mean = torch.empty(c, dtype=torch.float32, device=x.device)
     invstd = torch.empty(c, dtype=torch.float32, device=x.device)
     ws = workspace(lib.b200unet_bn_workspace_bytes(c), x.device)
@@ -265,7 +269,8 @@ def bn_fwd_train(x, gamma, beta, running_mean, running_var, momentum: float, eps
 
 
 def bn_fwd_eval(x, gamma, beta, running_mean, running_var, eps: float):
-    y = torch.empty_like(x)
+    n, h, w, c = x.shape
+    y = _nhwc_empty(n, h, w, c, x.device, isinstance(x, Split))
     vx, vy = view(x), view(y)
     check(_lib.load().b200unet_bn_fwd_eval(C.byref(vx), C.byref(vy), gamma.data_ptr(), beta.data_ptr(),
                                            running_mean.data_ptr(), running_var.data_ptr(), eps, stream_ptr()),

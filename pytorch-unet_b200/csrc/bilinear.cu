@@ -29,6 +29,17 @@ __device__ __forceinline__ void load_vec(const bf16* p, float (&f)[VEC]) {
     f[0] = bf2f(p[0]);
   }
 }
+// split tier (b200unet.h): value = hi + lo; lo == nullptr in the bf16 tier
+template <int VEC>
+__device__ __forceinline__ void load_vec_s(const bf16* hi, const bf16* lo, long long off, float (&f)[VEC]) {
+  load_vec<VEC>(hi + off, f);
+  if (VEC == 8 && lo) {
+    float t[VEC];
+    load_vec<VEC>(lo + off, t);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) f[j] += t[j];
+  }
+}
 template <int VEC>
 __device__ __forceinline__ void store_vec(bf16* p, const float (&f)[VEC]) {
   if (VEC == 8) {
@@ -57,13 +68,20 @@ __global__ void __launch_bounds__(256) bilinear_fwd_kernel(DView x, DView y) {
     src_taps(oh, x.h, h0, h1, a0, a1);
     src_taps(ow, x.w, w0, w1, b0, b1);
     float v00[VEC], v01[VEC], v10[VEC], v11[VEC], r[VEC];
-    load_vec<VEC>(x.p + x.off(n, h0, w0) + l * VEC, v00);
-    load_vec<VEC>(x.p + x.off(n, h0, w1) + l * VEC, v01);
-    load_vec<VEC>(x.p + x.off(n, h1, w0) + l * VEC, v10);
-    load_vec<VEC>(x.p + x.off(n, h1, w1) + l * VEC, v11);
+    load_vec_s<VEC>(x.p, x.lo, x.off(n, h0, w0) + l * VEC, v00);
+    load_vec_s<VEC>(x.p, x.lo, x.off(n, h0, w1) + l * VEC, v01);
+    load_vec_s<VEC>(x.p, x.lo, x.off(n, h1, w0) + l * VEC, v10);
+    load_vec_s<VEC>(x.p, x.lo, x.off(n, h1, w1) + l * VEC, v11);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) r[j] = a0 * (b0 * v00[j] + b1 * v01[j]) + a1 * (b0 * v10[j] + b1 * v11[j]);
-    store_vec<VEC>(y.p + y.off(n, oh, ow) + l * VEC, r);
+    const long long oo = y.off(n, oh, ow) + l * VEC;
+    store_vec<VEC>(y.p + oo, r);
+    if (VEC == 8 && y.lo) {
+      float t[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) t[j] = split_lo(r[j], bf2f(f2bf(r[j])));
+      store_vec<VEC>(y.lo + oo, t);
+    }
   }
 }
 
@@ -138,6 +156,8 @@ int b200unet_bilinear_up2x_fwd(const b200_view* x, const b200_view* y, void* str
   B200_REQUIRE(y->n == x->n && y->c == x->c && y->h == 2 * x->h && y->w == 2 * x->w,
                "bilinear_fwd: output extent must be 2x the input");
   const bool v8 = vec8_ok(*x) && vec8_ok(*y);
+  B200_REQUIRE((x->lo == nullptr) == (y->lo == nullptr), "bilinear_fwd: x and y must be of the same precision tier");
+  B200_REQUIRE(v8 || !x->lo, "bilinear_fwd: the split tier needs channel counts / strides that are multiples of 8");
   const long long total = view_pixels(*y) * (v8 ? y->c / 8 : y->c);
   if (v8)
     bilinear_fwd_kernel<8><<<stream_grid(total), 256, 0, as_stream(stream)>>>(dview(*x), dview(*y));

@@ -82,7 +82,7 @@ bn_apply_kernel(DView x, DView y, const float* __restrict__ gamma, const float* 
     float v[VEC];
     if (VEC == 8) {
       float t[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(x.p + x.off(n, ih, iw) + l * 8), t);
+      load8s(x.p, x.lo, x.off(n, ih, iw) + l * 8, t);
 #pragma unroll
       for (int j = 0; j < VEC; ++j) v[j] = t[j];
     } else {
@@ -99,7 +99,7 @@ bn_apply_kernel(DView x, DView y, const float* __restrict__ gamma, const float* 
       float t[8];
 #pragma unroll
       for (int j = 0; j < VEC; ++j) t[j] = v[j];
-      *reinterpret_cast<bf16x8*>(y.p + y.off(n, ih, iw) + l * 8) = pack8(t);
+      store8s(y.p, y.lo, y.off(n, ih, iw) + l * 8, t);
     } else {
       y.p[y.off(n, ih, iw) + l] = f2bf(v[0]);
     }
@@ -170,6 +170,8 @@ int b200unet_bn_fwd_train(const b200_view* x, const b200_view* y, const float* g
   B200_REQUIRE(view_ok(x) && view_ok(y) && same_extent(*x, *y) && gamma && beta && save_mean && save_invstd && workspace,
                "bn_fwd_train: bad arguments");
   B200_REQUIRE(workspace_bytes >= reduce_workspace_bytes(x->c, 2), "bn_fwd_train: workspace too small");
+  B200_REQUIRE((x->lo == nullptr) == (y->lo == nullptr), "bn_fwd_train: x and y must be of the same precision tier");
+  B200_REQUIRE(!x->lo || (vec8_ok(*x) && vec8_ok(*y)), "bn_fwd_train: the split tier needs channels / strides % 8 == 0");
   cudaStream_t st = as_stream(stream);
   ReducePlan pl;
   int r = launch_chan_reduce<2, false>(StatsF(), *x, nullptr, (float*)workspace, &pl, st);
@@ -192,6 +194,8 @@ int b200unet_bn_fwd_eval(const b200_view* x, const b200_view* y, const float* ga
                          const float* running_mean, const float* running_var, float eps, void* stream) {
   B200_REQUIRE(view_ok(x) && view_ok(y) && same_extent(*x, *y) && gamma && beta && running_mean && running_var,
                "bn_fwd_eval: bad arguments");
+  B200_REQUIRE((x->lo == nullptr) == (y->lo == nullptr), "bn_fwd_eval: x and y must be of the same precision tier");
+  B200_REQUIRE(!x->lo || (vec8_ok(*x) && vec8_ok(*y)), "bn_fwd_eval: the split tier needs channels / strides % 8 == 0");
   cudaStream_t st = as_stream(stream);
   const bool v8 = vec8_ok(*x) && vec8_ok(*y);
   const long long total = view_pixels(*x) * (v8 ? x->c / 8 : x->c);

@@ -34,7 +34,7 @@ chan_reduce_kernel(F f, DView a, DView b, int lanes, int tb, long long npix, flo
       float fa[VEC], fb[VEC];
       if (VEC == 8) {
         float t8[8];
-        unpack8(*reinterpret_cast<const bf16x8*>(a.p + a.off(n, ih, iw) + l * 8), t8);
+        load8s(a.p, a.lo, a.off(n, ih, iw) + l * 8, t8);  // `a` may be a split-tier tensor (forward statistics)
 #pragma unroll
         for (int j = 0; j < VEC; ++j) fa[j] = t8[j];
         if (HAS_B) {

@@ -37,18 +37,20 @@ constexpr int kNumSMsB200 = 148;
 // ------------------------------------------------------------------ device view (POD copy usable in kernels)
 struct DView {
   bf16* p;
+  bf16* lo;  // split tier: low-order plane (same geometry), else nullptr
   int n, h, w, c;
   long long sn, sh, sw;
   __host__ __device__ long long off(int in, int ih, int iw) const { return in * sn + ih * sh + iw * sw; }
 };
 inline DView dview(const b200_view& v) {
-  return DView{reinterpret_cast<bf16*>(v.ptr), v.n, v.h, v.w, v.c, v.stride_n, v.stride_h, v.stride_w};
+  return DView{reinterpret_cast<bf16*>(v.ptr), reinterpret_cast<bf16*>(v.lo), v.n, v.h, v.w, v.c,
+               v.stride_n, v.stride_h, v.stride_w};
 }
 
 // 16-byte vector path is usable on this view
 inline bool vec8_ok(const b200_view& v) {
-  return v.c % 8 == 0 && reinterpret_cast<uintptr_t>(v.ptr) % 16 == 0 && v.stride_w % 8 == 0 && v.stride_h % 8 == 0 &&
-         v.stride_n % 8 == 0;
+  return v.c % 8 == 0 && reinterpret_cast<uintptr_t>(v.ptr) % 16 == 0 && reinterpret_cast<uintptr_t>(v.lo) % 16 == 0 &&
+         v.stride_w % 8 == 0 && v.stride_h % 8 == 0 && v.stride_n % 8 == 0;
 }
 inline int stream_grid(long long total) {
   long long g = (total + 255) / 256;
@@ -79,6 +81,31 @@ __device__ __forceinline__ void unpack8(const bf16x8 p, float (&f)[8]) {
 }
 __device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
   return make_uint4(f2_to_bf2x(f[0], f[1]), f2_to_bf2x(f[2], f[3]), f2_to_bf2x(f[4], f[5]), f2_to_bf2x(f[6], f[7]));
+}
+
+// Split tier (b200unet.h): value = hi + lo.  The sum of the two planes is exact in fp32 (8 + 8 significant bits).
+__device__ __forceinline__ void load8s(const bf16* hi, const bf16* lo, long long off, float (&f)[8]) {
+  unpack8(*reinterpret_cast<const bf16x8*>(hi + off), f);
+  if (lo) {
+    float t[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(lo + off), t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] += t[j];
+  }
+}
+__device__ __forceinline__ float split_lo(float v, float hi) {  // residual plane; 0 where hi is inf / NaN
+  return fabsf(hi) < INFINITY ? v - hi : 0.f;
+}
+__device__ __forceinline__ void store8s(bf16* hi, bf16* lo, long long off, const float (&f)[8]) {
+  const bf16x8 h = pack8(f);
+  *reinterpret_cast<bf16x8*>(hi + off) = h;
+  if (lo) {
+    float t[8];
+    unpack8(h, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = split_lo(f[j], t[j]);
+    *reinterpret_cast<bf16x8*>(lo + off) = pack8(t);
+  }
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

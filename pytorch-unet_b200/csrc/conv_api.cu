@@ -15,6 +15,8 @@ int check_conv_fwd(const b200_conv_fwd_params* p) {
   const int k = p->taps == 9 ? 3 : 1;
   for (int i = 0; i < p->num_src; ++i) {
     B200_REQUIRE(view_ok(&p->src[i]), "conv_fwd: bad src[%d] view", i);
+    B200_REQUIRE((p->src[i].lo != nullptr) == (p->dst.lo != nullptr),
+                 "conv_fwd: sources and destination must be of the same precision tier (lo planes)");
     B200_REQUIRE(p->src[i].n == p->dst.n && p->src[i].h + 2 * p->pad - (k - 1) == p->dst.h &&
                      p->src[i].w + 2 * p->pad - (k - 1) == p->dst.w,
                  "conv_fwd: src[%d] extent %dx%d does not produce dst %dx%d", i, p->src[i].h, p->src[i].w, p->dst.h,
@@ -105,6 +107,7 @@ int b200unet_conv_fwd(const b200_conv_fwd_params* p, void* stream) {
   if ((r = resolve(p, umma_conv_fwd_ok, "conv_fwd", &impl))) return r;
   if (impl == B200_IMPL_UMMA) return umma_conv_fwd(p, as_stream(stream));
   if (p->impl == B200_IMPL_AUTO && smallc_conv_fwd_ok(p)) return smallc_conv_fwd(p, as_stream(stream));
+  B200_REQUIRE(!p->dst.lo, "conv_fwd: the split precision tier runs on the tcgen05 / first-layer kernels only");
   return direct_conv_fwd(p, as_stream(stream));
 }
 
@@ -138,8 +141,10 @@ int b200unet_conv_wgrad(const b200_conv_wgrad_params* p, void* workspace, size_t
 int b200unet_convt_fwd(const b200_convt_fwd_params* p, void* stream) {
   B200_REQUIRE(p && view_ok(&p->x) && view_ok(&p->y), "convt_fwd: bad views");
   B200_REQUIRE(p->y.n == p->x.n && p->y.h == 2 * p->x.h && p->y.w == 2 * p->x.w, "convt_fwd: y must be 2x x");
+  B200_REQUIRE((p->x.lo != nullptr) == (p->y.lo != nullptr), "convt_fwd: x and y must be of the same precision tier");
   int impl, r;
   if ((r = resolve(p, umma_convt_fwd_ok, "convt_fwd", &impl))) return r;
+  B200_REQUIRE(impl == B200_IMPL_UMMA || !p->y.lo, "convt_fwd: the split precision tier runs on the tcgen05 kernel only");
   return impl == B200_IMPL_UMMA ? umma_convt_fwd(p, as_stream(stream)) : direct_convt_fwd(p, as_stream(stream));
 }
 

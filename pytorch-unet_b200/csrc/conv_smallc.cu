@@ -54,7 +54,13 @@ smallc_fwd_kernel(DView src, DView dst, const float* __restrict__ w, const float
 #pragma unroll
       for (int j = 0; j < 6; ++j) {
         const int ix = ox0 + j - pad;
-        xin[j] = (yok && ix >= 0 && ix < src.w) ? bf2f(src.p[src.off(n, iy, ix) + c]) : 0.f;
+        float v = 0.f;
+        if (yok && ix >= 0 && ix < src.w) {
+          const long long so = src.off(n, iy, ix) + c;
+          v = bf2f(src.p[so]);
+          if (src.lo) v += bf2f(src.lo[so]);  // split tier: the image is carried as hi + lo
+        }
+        xin[j] = v;
       }
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
@@ -83,15 +89,15 @@ smallc_fwd_kernel(DView src, DView dst, const float* __restrict__ w, const float
       f[k] = acc[p][k] + bs[q4 * 16 + k];
       if (relu) f[k] = fmaxf(f[k], 0.f);
     }
-    bf16* o = dst.p + dst.off(n, oy, ox) + o_base + q4 * 16;
-    float lo[8], hi[8];
+    const long long oo = dst.off(n, oy, ox) + o_base + q4 * 16;
+    float f0[8], f1[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      lo[k] = f[k];
-      hi[k] = f[8 + k];
+      f0[k] = f[k];
+      f1[k] = f[8 + k];
     }
-    *reinterpret_cast<bf16x8*>(o) = pack8(lo);
-    *reinterpret_cast<bf16x8*>(o + 8) = pack8(hi);
+    store8s(dst.p, dst.lo, oo, f0);
+    store8s(dst.p, dst.lo, oo + 8, f1);
   }
 }
 
@@ -244,8 +250,8 @@ __global__ void smallc_wgrad_reduce_kernel(const float* __restrict__ partial, in
 constexpr int kScWgradBlocks = 2 * kNumSMsB200;
 
 static bool sc_aligned_out(const b200_view& v) {
-  return v.c % 16 == 0 && reinterpret_cast<uintptr_t>(v.ptr) % 16 == 0 && v.stride_w % 8 == 0 && v.stride_h % 8 == 0 &&
-         (v.n == 1 || v.stride_n % 8 == 0);
+  return v.c % 16 == 0 && reinterpret_cast<uintptr_t>(v.ptr) % 16 == 0 && reinterpret_cast<uintptr_t>(v.lo) % 16 == 0 &&
+         v.stride_w % 8 == 0 && v.stride_h % 8 == 0 && (v.n == 1 || v.stride_n % 8 == 0);
 }
 
 bool smallc_conv_fwd_ok(const b200_conv_fwd_params* p) {

@@ -23,6 +23,11 @@
 // memory transpose -> mask -> full-line global stores).
 // Accumulators: MB x BN fp32 columns in TMEM, double-buffered when 2*MB*BN <= 512 so the epilogue of tile i overlaps
 // the MMAs of tile i+1.  Optional CTA pairs (cluster of 2) fetch half of every weight tile each and multicast it.
+//
+// Split precision tier (b200unet.h): the forward kernels accept activations carried as hi + lo bf16 planes.  The K loop
+// then runs three operand passes into the same accumulator — hi(x)*hi(W), lo(x)*hi(W), hi(x)*lo(W); the dropped
+// lo*lo term is 2^-18 relative — simply as three times as many A sources against a weight tensor packed
+// {hi | hi | lo} along K, and the epilogue writes the fp32 result as two planes (hi = bf16(v), lo = bf16(v - hi)).
 #include <cstdlib>
 
 #include "conv_impl.h"
@@ -38,20 +43,23 @@ constexpr int kMaxNB = 8;     // B (weight tile) stages
 constexpr uint32_t kSmemBudget = 188 * 1024;   // A + B stages
 constexpr uint32_t kStageOutBytes = kEpiWarps * 4096;  // epilogue transpose buffers: per warp [32 rows][64 cols] bf16
 
+constexpr int kMaxA = 6;  // A sources: 2 concat sources x 3 split-tier passes, or the 4 convT sub-lattices
+
 struct TileMaps {
-  CUtensorMap a[4];
+  CUtensorMap a[kMaxA];
   CUtensorMap b;
 };
 
 struct UmmaArgs {
   int num_a;
-  int a_c[4];
-  int a_koff[4];
+  int a_c[kMaxA];
+  int a_koff[kMaxA];
   int taps, kx, kpad, pad;
   int P, TH, TW;
   int tiles_x, tiles_y, n_img, n_ntiles;
   int Ho, Wo, cout_total;
   DView dst[4];
+  bf16* dst_lo[4];  // split tier: low-order output planes (same geometry as dst), else nullptr
   const bf16* mask[4];
   int ndst, dst_c0;
   const float* bias;
@@ -334,7 +342,11 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
         const bool valid = ty < a.TH && tx < a.TW && oy < a.Ho && ox < a.Wo;
         const long long off = valid ? dst.off(t.n, oy, ox) + ch0 : -1;  // -1 = nothing to store for this position
         const uint32_t taddr = tmem_base + buf * (MB * BN) + mb * BN + lane_base;
-        {
+        bf16* const dlo = a.dst_lo[d];
+        // split tier: a second pass over the same accumulators writes the low-order plane (the TMEM read is repeated
+        // rather than keeping 64 values live across the store phase)
+#pragma unroll 1
+        for (int plane = 0; plane < (dlo ? 2 : 1); ++plane) {
           uint32_t v[CP];
           {
             uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
@@ -347,24 +359,40 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
           tmem_ld_wait();
           // row-owner side: convert this position's CP accumulators (ReLU folded into the conversion) and park them as
           // LPR 16-byte chunks; chunk j goes to slot j ^ (lane & (LPR-1)) so the 32 rows do not collide on banks
+          if (plane == 0) {
 #pragma unroll
-          for (int j = 0; j < LPR; ++j) {
-            uint4 c;
-            if (a.relu) {
-              c.x = pack_bf16x2_relu(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
-              c.y = pack_bf16x2_relu(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
-              c.z = pack_bf16x2_relu(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
-              c.w = pack_bf16x2_relu(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
-            } else {
-              c.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
-              c.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
-              c.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
-              c.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+            for (int j = 0; j < LPR; ++j) {
+              uint4 c;
+              if (a.relu) {
+                c.x = pack_bf16x2_relu(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+                c.y = pack_bf16x2_relu(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+                c.z = pack_bf16x2_relu(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+                c.w = pack_bf16x2_relu(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+              } else {
+                c.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+                c.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+                c.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+                c.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+              }
+              stg[lane * LPR + (j ^ (lane & (LPR - 1)))] = c;
             }
-            stg[lane * LPR + (j ^ (lane & (LPR - 1)))] = c;
+          } else {
+            // lo = bf16(v' - bf16(v')), v' = the (ReLU'd) fp32 result
+#pragma unroll
+            for (int j = 0; j < LPR; ++j) {
+              float r[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float x = __uint_as_float(v[8 * j + e]);
+                if (a.relu) x = fmaxf(x, 0.f);
+                r[e] = split_lo(x, bf2f(f2bf(x)));
+              }
+              stg[lane * LPR + (j ^ (lane & (LPR - 1)))] = pack8(r);
+            }
           }
           __syncwarp();
           // store side: lane (rsub, cch) moves chunk cch of rows rsub, rsub + RPI, ...
+          bf16* const dp = plane ? dlo : dst.p;
           const int col = col0 + cch * 8;
           const bool col_ok = t.n0 + col < a.cout_total;
           long long offs[LPR];
@@ -388,7 +416,7 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
                 for (int j = 0; j < 8; ++j) f[j] = m[j] > 0.f ? f[j] : 0.f;
                 c = pack8(f);
               }
-              *reinterpret_cast<uint4*>(dst.p + offs[i] + col) = c;
+              *reinterpret_cast<uint4*>(dp + offs[i] + col) = c;
             }
           }
           __syncwarp();
@@ -421,8 +449,15 @@ struct Plan {
 };
 
 static bool aligned_view(const b200_view& v) {
-  return v.c % 8 == 0 && reinterpret_cast<uintptr_t>(v.ptr) % 16 == 0 && v.stride_w % 8 == 0 && v.stride_h % 8 == 0 &&
-         (v.n == 1 || v.stride_n % 8 == 0);
+  return v.c % 8 == 0 && reinterpret_cast<uintptr_t>(v.ptr) % 16 == 0 && reinterpret_cast<uintptr_t>(v.lo) % 16 == 0 &&
+         v.stride_w % 8 == 0 && v.stride_h % 8 == 0 && (v.n == 1 || v.stride_n % 8 == 0);
+}
+
+static b200_view lo_plane(const b200_view& v) {  // the low-order plane of a split-tier view, as a plain view
+  b200_view l = v;
+  l.ptr = v.lo;
+  l.lo = nullptr;
+  return l;
 }
 
 static bool device_is_sm100() {
@@ -595,16 +630,25 @@ int umma_conv_fwd(const b200_conv_fwd_params* p, cudaStream_t st) {
   if (!make_plan(p->dst.h, p->dst.w, p->dst.n, halo, p->dst.c, 1, p->dst.c, &pl)) return fail(-1, "conv_fwd: no plan");
   TileMaps maps;
   UmmaArgs a{};
-  a.num_a = p->num_src;
-  int koff = 0;
-  for (int i = 0; i < p->num_src; ++i) {
-    int r = make_a_map(&maps.a[i], p->src[i], pl.P, pl.TH + halo);
-    if (r) return fail(r, "conv_fwd: tensor map for src[%d] failed (%d)", i, r);
-    a.a_c[i] = p->src[i].c;
-    a.a_koff[i] = koff;
-    koff += (p->src[i].c + 63) / 64 * 64;
+  // split tier: operand passes {hi(x) | lo(x) | hi(x)} against weights packed {hi(W) | hi(W) | lo(W)} along K
+  const bool split = p->dst.lo != nullptr;
+  const int passes = split ? 3 : 1;
+  int kpad = 0;
+  for (int i = 0; i < p->num_src; ++i) kpad += (p->src[i].c + 63) / 64 * 64;
+  a.num_a = passes * p->num_src;
+  for (int ps = 0; ps < passes; ++ps) {
+    int koff = ps * kpad;
+    for (int i = 0; i < p->num_src; ++i) {
+      const int j = ps * p->num_src + i;
+      int r = make_a_map(&maps.a[j], ps == 1 ? lo_plane(p->src[i]) : p->src[i], pl.P, pl.TH + halo);
+      if (r) return fail(r, "conv_fwd: tensor map for src[%d] failed (%d)", i, r);
+      a.a_c[j] = p->src[i].c;
+      a.a_koff[j] = koff;
+      koff += (p->src[i].c + 63) / 64 * 64;
+    }
   }
-  a.kpad = koff;
+  a.kpad = passes * kpad;
+  a.dst_lo[0] = (bf16*)p->dst.lo;
   int r = make_b_map(&maps.b, p->w_packed, p->dst.c, p->taps * a.kpad, pl.BN / pl.CL);
   if (r) return fail(r, "conv_fwd: weight tensor map failed (%d)", r);
   a.taps = p->taps;
@@ -677,7 +721,9 @@ int umma_conv_dgrad(const b200_conv_dgrad_params* p, cudaStream_t st) {
 // ------------------------------------------------------------------ ConvTranspose2d forward / backward-data
 static b200_view quadrant(const b200_view& big, int ab) {
   b200_view q = big;
-  q.ptr = (char*)big.ptr + ((int64_t)(ab >> 1) * big.stride_h + (int64_t)(ab & 1) * big.stride_w) * 2;
+  const int64_t shift = ((int64_t)(ab >> 1) * big.stride_h + (int64_t)(ab & 1) * big.stride_w) * 2;
+  q.ptr = (char*)big.ptr + shift;
+  if (big.lo) q.lo = (char*)big.lo + shift;
   q.h = big.h / 2;
   q.w = big.w / 2;
   q.stride_h = big.stride_h * 2;
@@ -699,11 +745,17 @@ int umma_convt_fwd(const b200_convt_fwd_params* p, cudaStream_t st) {
   if (!make_plan(p->x.h, p->x.w, p->x.n, 0, 4 * p->y.c, 4, p->y.c, &pl)) return fail(-1, "convt_fwd: no plan");
   TileMaps maps;
   UmmaArgs a{};
-  a.num_a = 1;
-  int r = make_a_map(&maps.a[0], p->x, pl.P, pl.TH);
-  if (r) return fail(r, "convt_fwd: tensor map for x failed (%d)", r);
-  a.a_c[0] = p->x.c;
-  a.kpad = (p->x.c + 63) / 64 * 64;
+  const bool split = p->y.lo != nullptr;  // see umma_conv_fwd
+  const int cpad = (p->x.c + 63) / 64 * 64;
+  a.num_a = split ? 3 : 1;
+  int r = 0;
+  for (int ps = 0; ps < a.num_a; ++ps) {
+    r = make_a_map(&maps.a[ps], ps == 1 ? lo_plane(p->x) : p->x, pl.P, pl.TH);
+    if (r) return fail(r, "convt_fwd: tensor map for x failed (%d)", r);
+    a.a_c[ps] = p->x.c;
+    a.a_koff[ps] = ps * cpad;
+  }
+  a.kpad = a.num_a * cpad;
   r = make_b_map(&maps.b, p->w_packed, 4 * p->y.c, a.kpad, pl.BN / pl.CL);
   if (r) return fail(r, "convt_fwd: weight tensor map failed (%d)", r);
   a.taps = 1;
@@ -715,7 +767,11 @@ int umma_convt_fwd(const b200_convt_fwd_params* p, cudaStream_t st) {
   a.cout_total = 4 * p->y.c;
   a.ndst = 4;
   a.dst_c0 = p->y.c;
-  for (int ab = 0; ab < 4; ++ab) a.dst[ab] = dview(quadrant(p->y, ab));
+  for (int ab = 0; ab < 4; ++ab) {
+    const b200_view q = quadrant(p->y, ab);
+    a.dst[ab] = dview(q);
+    a.dst_lo[ab] = (bf16*)q.lo;
+  }
   a.bias = p->bias;
   return launch_plan(maps, a, pl, st);
 }

@@ -88,6 +88,11 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadArgs a) {
           unpack8(*reinterpret_cast<const bf16x8*>(xp + v * 8), t);
 #pragma unroll
           for (int j = 0; j < VEC; ++j) xv[j] = t[j];
+          if (a.x.lo) {  // split tier (forward modes): x = hi + lo
+            unpack8(*reinterpret_cast<const bf16x8*>(a.x.lo + (xp - a.x.p) + v * 8), t);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) xv[j] += t[j];
+          }
         } else {
           xv[0] = bf2f(xp[v]);
         }
@@ -293,6 +298,8 @@ int launch_head(const HeadArgs& a, int blocks, cudaStream_t st) {
                   a.x.sn % 8 == 0 &&
                   (!a.dx.p || (reinterpret_cast<uintptr_t>(a.dx.p) % 16 == 0 && a.dx.sw % 8 == 0 && a.dx.sh % 8 == 0 &&
                                a.dx.sn % 8 == 0 && reinterpret_cast<uintptr_t>(a.mask) % 16 == 0));
+  if (a.x.lo && !(v8 && reinterpret_cast<uintptr_t>(a.x.lo) % 16 == 0))
+    return fail(-1, "head: the split tier needs channel counts / strides that are multiples of 8");
   const int vec = v8 ? 8 : 1;
   const int nvec = c / vec;
   const int chunks = (MODE == HEAD_BWD || MODE == HEAD_CE_BWD) ? (nvec + 7) / 8 : 1;

@@ -15,7 +15,12 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, DView dst) {
     const int ih = (int)(r / dst.w), iw = (int)(r - (long long)ih * dst.w);
     bf16* o = dst.p + dst.off(n, ih, iw);
     const float* s = src + (long long)n * dst.c * hw + r;
-    for (int c = 0; c < dst.c; ++c) o[c] = f2bf(s[c * hw]);
+    for (int c = 0; c < dst.c; ++c) {
+      const float v = s[c * hw];
+      const bf16 h = f2bf(v);
+      o[c] = h;
+      if (dst.lo) dst.lo[dst.off(n, ih, iw) + c] = f2bf(split_lo(v, bf2f(h)));
+    }
   }
 }
 
@@ -52,13 +57,16 @@ __global__ void nhwc_to_nchw_kernel(DView src, float* __restrict__ dst) {
 
 // ------------------------------------------------------------------ weight packing
 // conv fprop: out[o][tap][kpad]; source i occupies columns [koff_i, koff_i + src_c[i]) of kpad, zero elsewhere.
+// split = 1: the K axis is three copies of that layout, {hi(w) | hi(w) | lo(w)} (split precision tier, b200unet.h).
 __global__ void pack_conv_fprop_kernel(const float* __restrict__ w, bf16* __restrict__ out, int cout, int cin_total,
-                                       int taps, int kpad, int c0, int c0pad) {
-  const long long total = (long long)cout * taps * kpad;
+                                       int taps, int kpad, int c0, int c0pad, int split) {
+  const int kall = split ? 3 * kpad : kpad;
+  const long long total = (long long)cout * taps * kall;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(e % kpad);
-    const int tap = (int)((e / kpad) % taps);
-    const int o = (int)(e / ((long long)kpad * taps));
+    const int kk = (int)(e % kall);
+    const int seg = kk / kpad, k = kk - seg * kpad;
+    const int tap = (int)((e / kall) % taps);
+    const int o = (int)(e / ((long long)kall * taps));
     int c = -1;
     if (k < c0pad) {
       if (k < c0) c = k;
@@ -66,7 +74,9 @@ __global__ void pack_conv_fprop_kernel(const float* __restrict__ w, bf16* __rest
       const int k1 = k - c0pad;
       if (k1 < cin_total - c0) c = c0 + k1;
     }
-    out[e] = f2bf(c >= 0 ? w[((long long)o * cin_total + c) * taps + tap] : 0.f);
+    const float v = c >= 0 ? w[((long long)o * cin_total + c) * taps + tap] : 0.f;
+    const bf16 h = f2bf(v);
+    out[e] = seg < 2 ? h : f2bf(split_lo(v, bf2f(h)));
   }
 }
 
@@ -85,13 +95,17 @@ __global__ void pack_conv_dgrad_kernel(const float* __restrict__ w, bf16* __rest
 // convT fwd: out[(ab*cout + o)][cpad] = w[c][o][ab];  convT dgrad: out[c][ab][opad] = w[c][o][ab]
 __global__ void pack_convt_kernel(const float* __restrict__ w, bf16* __restrict__ out, int cin, int cout, int mode,
                                   int kp) {
-  if (mode == 0) {
-    const long long total = (long long)4 * cout * kp;
+  if (mode == 0 || mode == 2) {
+    const int kall = mode == 2 ? 3 * kp : kp;  // mode 2: {hi | hi | lo} along K (split precision tier)
+    const long long total = (long long)4 * cout * kall;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-      const int c = (int)(e % kp);
-      const int row = (int)(e / kp);
+      const int kk = (int)(e % kall);
+      const int seg = kk / kp, c = kk - seg * kp;
+      const int row = (int)(e / kall);
       const int ab = row / cout, o = row - ab * cout;
-      out[e] = f2bf(c < cin ? w[((long long)c * cout + o) * 4 + ab] : 0.f);
+      const float v = c < cin ? w[((long long)c * cout + o) * 4 + ab] : 0.f;
+      const bf16 h = f2bf(v);
+      out[e] = seg < 2 ? h : f2bf(split_lo(v, bf2f(h)));
     }
   } else {
     const long long total = (long long)cin * 4 * kp;
@@ -209,22 +223,23 @@ size_t b200unet_pack_conv_weight_bytes(int cout, int num_src, const int* src_c, 
   if (!src_c || num_src < 1 || num_src > 2) return 0;
   int cin = 0;
   for (int i = 0; i < num_src; ++i) cin += src_c[i];
-  if (mode == 0) return (size_t)cout * taps * conv_kpad(num_src, src_c) * 2;
+  if (mode == 0 || mode == 2) return (size_t)cout * taps * conv_kpad(num_src, src_c) * 2 * (mode == 2 ? 3 : 1);
   return (size_t)cin * taps * ((cout + 63) / 64 * 64) * 2;
 }
 
 int b200unet_pack_conv_weight(const float* w, int cout, int num_src, const int* src_c, int taps, int mode, void* out,
                               void* stream) {
-  B200_REQUIRE(w && out && src_c && num_src >= 1 && num_src <= 2 && (taps == 1 || taps == 9) && cout > 0,
+  B200_REQUIRE(w && out && src_c && num_src >= 1 && num_src <= 2 && (taps == 1 || taps == 9) && cout > 0 && mode >= 0 &&
+                   mode <= 2,
                "pack_conv_weight: bad arguments");
   int cin = 0;
   for (int i = 0; i < num_src; ++i) cin += src_c[i];
-  if (mode == 0) {
+  if (mode == 0 || mode == 2) {
     const int kpad = conv_kpad(num_src, src_c);
     const int c0 = src_c[0], c0pad = (c0 + 63) / 64 * 64;
-    const long long total = (long long)cout * taps * kpad;
+    const long long total = (long long)cout * taps * kpad * (mode == 2 ? 3 : 1);
     pack_conv_fprop_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(w, (bf16*)out, cout, cin, taps, kpad,
-                                                                                c0, c0pad);
+                                                                                c0, c0pad, mode == 2);
   } else {
     const int opad = (cout + 63) / 64 * 64;
     const long long total = (long long)cin * taps * opad;
@@ -234,14 +249,14 @@ int b200unet_pack_conv_weight(const float* w, int cout, int num_src, const int* 
 }
 
 size_t b200unet_pack_convt_weight_bytes(int cin, int cout, int mode) {
-  if (mode == 0) return (size_t)4 * cout * ((cin + 63) / 64 * 64) * 2;
+  if (mode == 0 || mode == 2) return (size_t)4 * cout * ((cin + 63) / 64 * 64) * 2 * (mode == 2 ? 3 : 1);
   return (size_t)cin * 4 * ((cout + 63) / 64 * 64) * 2;
 }
 
 int b200unet_pack_convt_weight(const float* w, int cin, int cout, int mode, void* out, void* stream) {
-  B200_REQUIRE(w && out && cin > 0 && cout > 0, "pack_convt_weight: bad arguments");
-  const int kp = mode == 0 ? (cin + 63) / 64 * 64 : (cout + 63) / 64 * 64;
-  const long long total = mode == 0 ? (long long)4 * cout * kp : (long long)cin * 4 * kp;
+  B200_REQUIRE(w && out && cin > 0 && cout > 0 && mode >= 0 && mode <= 2, "pack_convt_weight: bad arguments");
+  const int kp = mode != 1 ? (cin + 63) / 64 * 64 : (cout + 63) / 64 * 64;
+  const long long total = mode != 1 ? (long long)4 * cout * kp * (mode == 2 ? 3 : 1) : (long long)cin * 4 * kp;
   pack_convt_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(w, (bf16*)out, cin, cout, mode, kp);
   return check_launch("pack_convt_weight");
 }

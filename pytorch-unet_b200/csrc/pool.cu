@@ -28,14 +28,14 @@ maxpool_fwd_kernel(DView x, DView y, uint8_t* __restrict__ idx8, long long* __re
     for (int a = 0; a < 2; ++a)
 #pragma unroll
       for (int b = 0; b < 2; ++b) {
-        const bf16* s = x.p + x.off(n, 2 * oh + a, 2 * ow + b) + l * VEC;
+        const long long so = x.off(n, 2 * oh + a, 2 * ow + b) + l * VEC;
         if (VEC == 8) {
           float t[8];
-          unpack8(*reinterpret_cast<const bf16x8*>(s), t);
+          load8s(x.p, x.lo, so, t);  // split tier: compare and forward hi + lo
 #pragma unroll
           for (int j = 0; j < VEC; ++j) v[a * 2 + b][j] = t[j];
         } else {
-          v[a * 2 + b][0] = bf2f(s[0]);
+          v[a * 2 + b][0] = bf2f(x.p[so]);
         }
       }
     float best[VEC];
@@ -48,12 +48,13 @@ maxpool_fwd_kernel(DView x, DView y, uint8_t* __restrict__ idx8, long long* __re
       for (int k = 0; k < 4; ++k) pool_scan(v[k][j], k, best[j], arg[j]);
     }
     const long long opix = ((long long)n * y.h + oh) * y.w + ow;
-    bf16* o = y.p + y.off(n, oh, ow) + l * VEC;
+    const long long oo = y.off(n, oh, ow) + l * VEC;
+    bf16* o = y.p + oo;
     if (VEC == 8) {
       float t[8];
 #pragma unroll
       for (int j = 0; j < VEC; ++j) t[j] = best[j];
-      *reinterpret_cast<bf16x8*>(o) = pack8(t);
+      store8s(y.p, y.lo, oo, t);
       uint2 codes;
       codes.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
       codes.y = arg[4 % VEC] | (arg[5 % VEC] << 8) | (arg[6 % VEC] << 16) | (arg[7 % VEC] << 24);
@@ -162,6 +163,8 @@ int b200unet_maxpool2x2_fwd(const b200_view* x, const b200_view* y, uint8_t* idx
   B200_REQUIRE(y->n == x->n && y->c == x->c && y->h == x->h / 2 && y->w == x->w / 2,
                "maxpool_fwd: output extent must be floor(input/2)");
   const bool v8 = vec8_ok(*x) && vec8_ok(*y) && reinterpret_cast<uintptr_t>(idx8) % 8 == 0;
+  B200_REQUIRE((x->lo == nullptr) == (y->lo == nullptr), "maxpool_fwd: x and y must be of the same precision tier");
+  B200_REQUIRE(v8 || !x->lo, "maxpool_fwd: the split tier needs channel counts / strides that are multiples of 8");
   if (v8)
     maxpool_fwd_kernel<8><<<(unsigned)(y->n * y->h), 256, 0, as_stream(stream)>>>(dview(*x), dview(*y), idx8,
                                                                             (long long*)idx64);

@@ -2,9 +2,10 @@
   (1) the committed golden vectors produced by the unmodified reference on CPU fp32 (tests/golden), and
   (2) the CPU oracle (oracle/unet_oracle.py) on fresh seeded inputs at sizes it finishes in seconds.
 Tolerances are BASELINE.json's: logits rel-L2 <= 1e-2, weight gradients rel-L2 <= 2e-2 on the concatenated
-gradient vector (per-tensor figures are printed), argmax agreement >= 99.9 %.  BatchNorm configurations are
-reported against the same numbers; SURVEY.md §7.4 measured what plain bf16 storage can reach there, and the
-asserted bound for them is the looser one written below.
+gradient vector (per-tensor figures are printed), argmax agreement >= 99.9 %.  BatchNorm graphs run in the module's
+split precision tier by default (forward activations / operands as hi + lo bf16 planes) and are held to the same
+tolerances; their plain-bf16 tier is also exercised, against the looser bound SURVEY.md §7.4 measured for bf16
+storage (written below).
 """
 import glob
 import json
@@ -22,10 +23,14 @@ pytestmark = pytest.mark.gpu
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
 
 TOL_LOGITS, TOL_GRAD, TOL_ARGMAX = 1e-2, 2e-2, 0.999          # BASELINE.json north_star (paper graph, no BatchNorm)
-TOL_GRAD_DEEP = 4e-2                                            # Deep decoder without BatchNorm (not a BASELINE config)
-# bf16 activation storage through BatchNorm (mean removal amplifies rounding): SURVEY §7.4 measured 2e-2..1e-1 on the
-# logits and 5e-2..3e-1 on the gradients for an ideal bf16 pipeline; these configs are bounded against the fp32
-# reference loosely and against the bf16-storage-emulating oracle tightly (TOL_EMU_*), which is the logic check.
+# Deep decoder (unet.py:60, 4..64-channel layers): logits / argmax meet the north_star bound.  The gradient of these
+# narrow graphs amplifies any forward perturbation ~100x through ReLU / arg-max flips: the fp32 oracle against the same
+# oracle in fp64 already differs by 1.8e-3 at BASELINE config 5's size, and a CPU emulation with ~16-bit operands in
+# forward AND backward gives 3.4e-2 at the test size / 1.9e-2 at config 5's (experiments/precision_emu*.py).  Held to
+# 4e-2 without BatchNorm and 6e-2 with it; the measured values are printed.
+TOL_GRAD_DEEP, TOL_GRAD_DEEP_BN = 4e-2, 6e-2
+# plain-bf16 tier on BatchNorm graphs (precision="bf16"; not the default): SURVEY §7.4 measured 2e-2..1e-1 on the
+# logits and 5e-2..3e-1 on the gradients for an ideal bf16 pipeline.
 TOL_LOGITS_BN, TOL_GRAD_BN, TOL_ARGMAX_BN = 1.2e-1, 4e-1, 0.92
 TOL_EMU_LOGITS, TOL_EMU_GRAD = 2e-2, 8e-2
 
@@ -68,11 +73,12 @@ def grad_errors(grads, ref_grads):
     return rel_l2(got, want), worst, per[worst]
 
 
-def compare(name, spec, logits, loss, grads, ref_logits, ref_loss, ref_grads):
-    """Against the fp32 reference (golden vectors / fp32 oracle)."""
-    bn, deep = spec["batch_norm"], spec["up_block"] == "deep"
+def compare(name, spec, logits, loss, grads, ref_logits, ref_loss, ref_grads, tier="auto"):
+    """Against the fp32 reference (golden vectors / fp32 oracle).  tier = the module's `precision` argument."""
+    deep = spec["up_block"] == "deep"
+    bn = spec["batch_norm"] and tier == "bf16"  # loose bounds only for BatchNorm graphs forced into the bf16 tier
     tl, ta = (TOL_LOGITS_BN, TOL_ARGMAX_BN) if bn else (TOL_LOGITS, TOL_ARGMAX)
-    tg = TOL_GRAD_BN if bn else (TOL_GRAD_DEEP if deep else TOL_GRAD)
+    tg = TOL_GRAD_BN if bn else ((TOL_GRAD_DEEP_BN if spec["batch_norm"] else TOL_GRAD_DEEP) if deep else TOL_GRAD)
     if logits is not None:
         e = rel_l2(logits, ref_logits)
         raw, clear = argmax_agreement(logits, ref_logits)
@@ -82,7 +88,7 @@ def compare(name, spec, logits, loss, grads, ref_logits, ref_loss, ref_grads):
     assert abs(loss - ref_loss) <= 2e-2 * max(1.0, abs(ref_loss)) * (10 if bn else 1)
     eg, worst, ew = grad_errors(grads, ref_grads)
     print(f"[{name}] vs fp32 reference: grad rel-L2 (all weights) {eg:.3e}; worst tensor {worst} {ew:.3e}")
-    if not (bn and deep):  # BatchNorm + 4-channel layers: reported, bounded through the emulating oracle instead
+    if not (bn and deep):  # bf16 tier on BatchNorm + 4-channel layers: reported only
         assert eg <= tg
 
 
@@ -102,29 +108,46 @@ def compare_emulated(name, spec_obj, sd, x, y, logits, grads):
     assert spec_obj.batch_norm or eg <= TOL_EMU_GRAD
 
 
-@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
-@pytest.mark.parametrize("fused_loss", [False, True], ids=["logits+F.cross_entropy", "fused-loss"])
-def test_against_reference_golden(path, fused_loss):
+def _golden_step(path, fused_loss, tier):
     z = np.load(path)
     spec = json.loads(bytes(z["spec"]).decode())
     sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
-    model = build(spec).cuda()
+    model = build(spec, precision=tier).cuda()
+    assert model.precision == ("bf16" if tier == "bf16" or not spec["batch_norm"] else "split")
     model.load_state_dict(sd)
     model.train()
     x, y = torch.from_numpy(z["x"]).cuda(), torch.from_numpy(z["y"]).cuda()
     logits, loss, grads = run_step(model, x, y, fused_loss)
     ref_grads = {k[5:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("grad/")}
-    compare(os.path.basename(path), spec, logits, loss, grads, torch.from_numpy(z["logits"]), float(z["loss"]), ref_grads)
-    if not fused_loss:
+    compare(os.path.basename(path), spec, logits, loss, grads, torch.from_numpy(z["logits"]), float(z["loss"]), ref_grads,
+            tier)
+    if not fused_loss and model.precision == "bf16":
         compare_emulated(os.path.basename(path), O.UNetSpec(**spec), sd, torch.from_numpy(z["x"]), torch.from_numpy(z["y"]),
                          logits, grads)
     if spec["batch_norm"]:
         after = model.state_dict()
+        rtol, atol = (5e-2, 5e-3) if model.precision == "bf16" else (1e-3, 1e-4)
         for k in z.files:
             if k.startswith("sd_after/") and "running" in k:
-                assert torch.allclose(after[k[9:]].cpu(), torch.from_numpy(z[k]), rtol=5e-2, atol=5e-3), k
+                assert torch.allclose(after[k[9:]].cpu(), torch.from_numpy(z[k]), rtol=rtol, atol=atol), k
             if k.startswith("sd_after/") and "num_batches" in k:
                 assert int(after[k[9:]]) == int(z[k])
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+@pytest.mark.parametrize("fused_loss", [False, True], ids=["logits+F.cross_entropy", "fused-loss"])
+def test_against_reference_golden(path, fused_loss):
+    _golden_step(path, fused_loss, "auto")
+
+
+GOLDEN_BN = [p for p in GOLDEN if json.loads(bytes(np.load(p)["spec"]).decode())["batch_norm"]]
+
+
+@pytest.mark.parametrize("path", GOLDEN_BN, ids=[os.path.basename(p)[:-4] for p in GOLDEN_BN])
+def test_batchnorm_graphs_in_the_bf16_tier(path):
+    """precision='bf16' on BatchNorm graphs stays available (one tensor-core pass, half the activation traffic); it is
+    bounded by what bf16 storage can reach there."""
+    _golden_step(path, False, "bf16")
 
 
 ORACLE_CASES = {
@@ -157,7 +180,8 @@ def test_against_cpu_oracle(name):
     model.train()
     logits, loss, grads = run_step(model, x.cuda(), y.cuda(), fused_loss=False)
     compare(name, spec.__dict__, logits, loss, grads, ref_logits, float(ref_loss), ref_grads)
-    compare_emulated(name, spec, sd, x, y, logits, grads)
+    if model.precision == "bf16":
+        compare_emulated(name, spec, sd, x, y, logits, grads)
 
 
 def test_eval_mode_and_no_grad_match_oracle():
@@ -175,7 +199,7 @@ def test_eval_mode_and_no_grad_match_oracle():
     model.eval()
     with torch.no_grad():
         out = model(x.cuda())
-    assert rel_l2(out.cpu(), ref) < 3e-2
+    assert rel_l2(out.cpu(), ref) < 1e-3  # split tier (BatchNorm graph)
     assert torch.equal(model.state_dict()["down_path.0.block.2.running_mean"].cpu(), sd["down_path.0.block.2.running_mean"])
 
 
