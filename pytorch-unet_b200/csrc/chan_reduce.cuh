@@ -12,9 +12,34 @@ constexpr int kReduceThreads = 256;
 // Functor contract:  template<int VEC> __device__ void operator()(const float (&a)[VEC], const float (&b)[VEC],
 //                                                                  float (&acc)[NV][VEC]) const;
 // `b` is only loaded when HAS_B.
+template <int VEC, bool HAS_B>
+__device__ __forceinline__ void reduce_load(const DView& a, const DView& b, long long oa, long long ob, float (&fa)[VEC],
+                                            float (&fb)[VEC]) {
+  if (VEC == 8) {
+    float t8[8];
+    load8s(a.p, a.lo, oa, t8);  // `a` may be a split-tier tensor (forward statistics)
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) fa[j] = t8[j];
+    if (HAS_B) {
+      unpack8(*reinterpret_cast<const bf16x8*>(b.p + ob), t8);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) fb[j] = t8[j];
+    }
+  } else {
+    fa[0] = bf2f(a.p[oa]);
+    if (HAS_B) fb[0] = bf2f(b.p[ob]);
+  }
+  if (!HAS_B) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) fb[j] = 0.f;
+  }
+}
+
+// `dense` (both views contiguous over their pixels: offset = pixel * stride_w): no index arithmetic beyond one multiply,
+// and four pixels in flight per thread — one 16-byte load per dependent loop iteration left this kernel at ~2.8 TB/s.
 template <int VEC, int NV, bool HAS_B, class F>
 __global__ void __launch_bounds__(kReduceThreads)
-chan_reduce_kernel(F f, DView a, DView b, int lanes, int tb, long long npix, float* __restrict__ partial) {
+chan_reduce_kernel(F f, DView a, DView b, int lanes, int tb, long long npix, int dense, float* __restrict__ partial) {
   extern __shared__ float red[];  // [NV*VEC][tb]
   const int t = threadIdx.x;
   float acc[NV][VEC];
@@ -26,31 +51,32 @@ chan_reduce_kernel(F f, DView a, DView b, int lanes, int tb, long long npix, flo
   if (t < tb) {
     const int ps = t / lanes, l = t - ps * lanes;
     const int pb = tb / lanes;
-    const long long hw = (long long)a.h * a.w;
-    for (long long p = (long long)blockIdx.x * pb + ps; p < npix; p += (long long)gridDim.x * pb) {
-      const int n = (int)(p / hw);
-      const int r = (int)(p - n * hw);
-      const int ih = r / a.w, iw = r - ih * a.w;
-      float fa[VEC], fb[VEC];
-      if (VEC == 8) {
-        float t8[8];
-        load8s(a.p, a.lo, a.off(n, ih, iw) + l * 8, t8);  // `a` may be a split-tier tensor (forward statistics)
+    const long long step = (long long)gridDim.x * pb;
+    long long p = (long long)blockIdx.x * pb + ps;
+    if (dense) {
+      const long long lo = (long long)l * VEC;
+      for (; p + 3 * step < npix; p += 4 * step) {
+        float fa[4][VEC], fb[4][VEC];
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) fa[j] = t8[j];
-        if (HAS_B) {
-          unpack8(*reinterpret_cast<const bf16x8*>(b.p + b.off(n, ih, iw) + l * 8), t8);
+        for (int u = 0; u < 4; ++u) reduce_load<VEC, HAS_B>(a, b, (p + u * step) * a.sw + lo, (p + u * step) * b.sw + lo, fa[u], fb[u]);
 #pragma unroll
-          for (int j = 0; j < VEC; ++j) fb[j] = t8[j];
-        }
-      } else {
-        fa[0] = bf2f(a.p[a.off(n, ih, iw) + l]);
-        if (HAS_B) fb[0] = bf2f(b.p[b.off(n, ih, iw) + l]);
+        for (int u = 0; u < 4; ++u) f(fa[u], fb[u], acc, l * VEC);
       }
-      if (!HAS_B) {
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) fb[j] = 0.f;
+      for (; p < npix; p += step) {
+        float fa[VEC], fb[VEC];
+        reduce_load<VEC, HAS_B>(a, b, p * a.sw + lo, p * b.sw + lo, fa, fb);
+        f(fa, fb, acc, l * VEC);
       }
-      f(fa, fb, acc, l * VEC);
+    } else {
+      const long long hw = (long long)a.h * a.w;
+      for (; p < npix; p += step) {
+        const int n = (int)(p / hw);
+        const int r = (int)(p - n * hw);
+        const int ih = r / a.w, iw = r - ih * a.w;
+        float fa[VEC], fb[VEC];
+        reduce_load<VEC, HAS_B>(a, b, a.off(n, ih, iw) + l * VEC, b.off(n, ih, iw) + l * VEC, fa, fb);
+        f(fa, fb, acc, l * VEC);
+      }
     }
 #pragma unroll
     for (int v = 0; v < NV; ++v)
@@ -116,12 +142,16 @@ inline int launch_chan_reduce(F f, const b200_view& a, const b200_view* b, float
   if (!plan_reduce(a, b, NV, pl)) return fail(-1, "channel reduction: unsupported channel count %d", a.c);
   DView da = dview(a), db = b ? dview(*b) : da;
   const long long npix = view_pixels(a);
+  auto pix_dense = [](const b200_view& v) {
+    return v.stride_h == (int64_t)v.w * v.stride_w && (v.n == 1 || v.stride_n == (int64_t)v.h * v.stride_h);
+  };
+  const int dense = pix_dense(a) && (!b || pix_dense(*b));
   if (pl->vec == 8)
     chan_reduce_kernel<8, NV, HAS_B, F><<<pl->blocks, kReduceThreads, pl->smem, st>>>(f, da, db, pl->lanes, pl->tb,
-                                                                                     npix, partial);
+                                                                                     npix, dense, partial);
   else
     chan_reduce_kernel<1, NV, HAS_B, F><<<pl->blocks, kReduceThreads, pl->smem, st>>>(f, da, db, pl->lanes, pl->tb,
-                                                                                     npix, partial);
+                                                                                     npix, dense, partial);
   return check_launch("chan_reduce");
 }
 

@@ -1,8 +1,9 @@
 """BASELINE.json configurations at their FULL sizes on the B200 (through the drop-in module -> C ABI).
 
 config 1 (paper default, batch 1, 572x572) is small enough for the CPU oracle: logits / loss / gradients are compared
-against it with north_star's tolerances.  For the larger configurations the oracle would take minutes, so they are
-checked through size-independent properties of the training step:
+against it with north_star's tolerances; so are the two BatchNorm configurations (2 and 5, full batch: the batch
+statistics are part of the result), which run in the module's split precision tier.  For the larger configurations the
+oracle would take minutes, so they are checked through size-independent properties of the training step:
   * run-to-run bit-exactness (every kernel reduces in a fixed order),
   * linearity of the backward pass in the upstream gradient,
   * batch additivity: gradients on [a; b] equal the pixel-weighted mean of the gradients on a and on b (no BatchNorm) —
@@ -62,6 +63,46 @@ def test_config1_paper_default_batch1_572_vs_oracle():
           f"loss {float(loss):.6f} vs {float(ref_loss):.6f}")
     assert e <= 1e-2 and eg <= 2e-2 and agree >= 0.999   # BASELINE.json north_star tolerances
     assert abs(float(loss) - float(ref_loss)) <= 1e-3 * max(1.0, abs(float(ref_loss)))
+
+
+BN_FULL = {
+    # name: (ctor args, up_block, batch, H, W, gradient tolerance)
+    "config2_same_bn_upsample_b16_256": ((1, 2, 5, 6, True, True, "upsample"), "paper", 16, 256, 256, 2e-2),
+    # Deep decoder with 4..64 channels: gradient bound as in test_unet_gpu.py (TOL_GRAD_DEEP_BN), value printed
+    "config5_deep_feature_b12_192x640": ((3, 6, 5, 2, True, True, "upsample", True), "deep", 12, 192, 640, 6e-2),
+}
+
+
+@pytest.mark.parametrize("name", list(BN_FULL))
+def test_batchnorm_configs_full_size_vs_oracle(name):
+    import b200unet
+    args, up_block, b, h, w, tol_grad = BN_FULL[name]
+    spec = O.UNetSpec(*args[:7], non_neg=(args[7] if len(args) > 7 else False), up_block=up_block)
+    sd = O.init_params(spec, seed=0)
+    torch.manual_seed(2)
+    x = (torch.rand if name.startswith("config5") else torch.randn)(b, args[0], h, w)
+    c = x[:, 0].contiguous()
+    qs = torch.quantile(c.flatten()[:1 << 20], torch.linspace(0, 1, spec.n_classes + 1)[1:-1])
+    y = torch.bucketize(c, qs)
+    ref_logits, ref_loss, ref_grads, ref_stats = O.loss_and_grads(sd, x, y, spec)
+    model = b200unet.UNet(*args, up_block=up_block).cuda().train()
+    assert model.precision == "split"
+    model.load_state_dict(sd)
+    logits = model(x.cuda())
+    loss = F.cross_entropy(logits, y.cuda())
+    loss.backward()
+    e = rel_l2(logits.detach().cpu(), ref_logits)
+    agree = float((logits.argmax(1).cpu() == ref_logits.argmax(1)).float().mean())
+    keys = list(ref_grads)
+    eg = rel_l2(torch.cat([dict(model.named_parameters())[k].grad.cpu().flatten() for k in keys]),
+                torch.cat([ref_grads[k].flatten() for k in keys]))
+    print(f"[{name}] logits rel-L2 {e:.3e} argmax agreement {agree:.5f} grad rel-L2 {eg:.3e} "
+          f"loss {float(loss):.6f} vs {float(ref_loss):.6f}")
+    assert e <= 1e-2 and agree >= 0.999 and eg <= tol_grad
+    assert abs(float(loss) - float(ref_loss)) <= 1e-4 * max(1.0, abs(float(ref_loss)))
+    after = model.state_dict()
+    for k, v in ref_stats.items():
+        assert torch.allclose(after[k].cpu(), v, rtol=1e-3, atol=1e-5), k
 
 
 FULL = {
