@@ -14,6 +14,7 @@
  *   head_fwd / head_bwd                  nn.Conv2d(k=1) head [+ReLU]                       unet.py:65-71, 84
  *   head_ce_fwd / head_ce_bwd            head fused with F.cross_entropy                   README.md:58
  *   nchw_f32_to_nhwc_bf16, nhwc_bf16_to_nchw_f32, pack_*   boundary layout / precision transforms
+ *   adam_plan / adam_upload / adam_step               torch.optim.Adam(model.parameters()).step()       README.md:49, run.py:71
  *
  * Conventions
  *   - Activations and activation gradients are bf16, NHWC ("pixels x channels"), described by b200_view.  A
@@ -244,6 +245,36 @@ int b200unet_im2col3x3(const b200_view* src, const b200_view* dst, int pad, void
 int b200unet_channel_sum(const b200_view* dz, float* out, void* workspace, size_t workspace_bytes, void* stream);
 /* y = (mask > 0) ? x : 0, in place allowed; mask laid out like y */
 int b200unet_relu_mask(const b200_view* x, const void* mask, const b200_view* y, void* stream);
+
+/* ---- torch.optim.Adam step (README.md:49, run.py:71; amsgrad = false, maximize = false) over all parameter tensors
+ * in ONE launch, fused with the refresh of the packed bf16 operand copies.
+ * One job per parameter tensor.  kind 0: plain tensor.  kind 1: conv weight [dim0 = cout][dim1 = cin_total][taps];
+ * kind 2: ConvTranspose2d weight [dim0 = cin][dim1 = cout][taps = 4].  For kinds 1 / 2, pack_fwd / pack_dgrad (either may
+ * be NULL) are buffers in exactly the layouts of pack_conv_weight / pack_convt_weight modes 0 (or 2 when split != 0) /
+ * 1, whose padding entries the CALLER zeroed once; the kernel rewrites every real entry from the updated weights.
+ * step_dev: device float holding the update count INCLUDING this update (torch's bias corrections 1 - beta^step
+ * are evaluated in double on the device, so a captured CUDA graph keeps counting).
+ * adam_plan fills block0 / nblocks of a HOST job array and returns the grid size; adam_upload writes the array into
+ * device memory (jobs_dev, num_jobs * sizeof(b200_adam_job) bytes) on the stream — the jobs travel as kernel
+ * arguments, so there is no staging buffer to keep alive and the upload is graph-capturable.                  */
+typedef struct {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  void* pack_fwd;
+  void* pack_dgrad;
+  int64_t numel;
+  int32_t kind;
+  int32_t dim0, dim1, taps;
+  int32_t src0_c; /* kind 1: channels of concat source 0 (= dim1 with a single source) */
+  int32_t split;  /* pack_fwd is in the split-tier layout {hi | hi | lo} */
+  int32_t block0, nblocks;
+} b200_adam_job;
+int b200unet_adam_plan(b200_adam_job* jobs_host, int num_jobs);
+int b200unet_adam_upload(b200_adam_job* jobs_dev, const b200_adam_job* jobs_host, int num_jobs, void* stream);
+int b200unet_adam_step(const b200_adam_job* jobs_dev, int num_jobs, int total_blocks, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, const float* step_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -54,6 +54,15 @@ class ConvTWgradParams(C.Structure):
     _fields_ = [("x", View), ("dy", View), ("dw_f32", C.c_void_p), ("db_f32", C.c_void_p), ("impl", C.c_int32)]
 
 
+class AdamJob(C.Structure):
+    """b200_adam_job"""
+
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("pack_fwd", C.c_void_p), ("pack_dgrad", C.c_void_p), ("numel", C.c_int64), ("kind", C.c_int32),
+                ("dim0", C.c_int32), ("dim1", C.c_int32), ("taps", C.c_int32), ("src0_c", C.c_int32),
+                ("split", C.c_int32), ("block0", C.c_int32), ("nblocks", C.c_int32)]
+
+
 _VP = C.POINTER(View)
 _P = C.c_void_p
 _I = C.c_int
@@ -103,6 +112,9 @@ SIGNATURES = {
     "b200unet_im2col3x3": (_I, [_VP, _VP, _I, _P]),
     "b200unet_channel_sum": (_I, [_VP, _P, _P, _SZ, _P]),
     "b200unet_relu_mask": (_I, [_VP, _P, _VP, _P]),
+    "b200unet_adam_plan": (_I, [C.POINTER(AdamJob), _I]),
+    "b200unet_adam_upload": (_I, [_P, C.POINTER(AdamJob), _I, _P]),
+    "b200unet_adam_step": (_I, [_P, _I, _I, _F, _F, _F, _F, _F, _P, _P]),
 }
 
 _lib = None

@@ -70,25 +70,31 @@ def im2col3x3(x: torch.Tensor, pad: int) -> torch.Tensor:
     return out
 
 
-def pack_conv_weight(w: torch.Tensor, src_c: Sequence[int], mode: int) -> torch.Tensor:
+def _pack_out(nbytes: int, device, out: Optional[torch.Tensor]) -> torch.Tensor:
+    if out is not None and out.numel() == nbytes // 2 and out.dtype == torch.bfloat16:
+        return out
+    return torch.empty(nbytes // 2, dtype=torch.bfloat16, device=device)
+
+
+def pack_conv_weight(w: torch.Tensor, src_c: Sequence[int], mode: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """fp32 [cout][cin][k][k] -> bf16 GEMM operand (mode 0: fprop, 1: dgrad, 2: fprop of the split tier)."""
     lib = _lib.load()
     cout, cin, k, _ = w.shape
     assert sum(src_c) == cin and w.dtype == torch.float32 and w.is_contiguous()
     arr = (C.c_int * len(src_c))(*src_c)
     nbytes = lib.b200unet_pack_conv_weight_bytes(cout, len(src_c), arr, k * k, mode)
-    out = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
+    out = _pack_out(nbytes, w.device, out)
     check(lib.b200unet_pack_conv_weight(w.data_ptr(), cout, len(src_c), arr, k * k, mode, out.data_ptr(),
                                         stream_ptr()), "pack_conv_weight")
     return out
 
 
-def pack_convt_weight(w: torch.Tensor, mode: int) -> torch.Tensor:
+def pack_convt_weight(w: torch.Tensor, mode: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     lib = _lib.load()
     cin, cout = w.shape[0], w.shape[1]
     assert w.dtype == torch.float32 and w.is_contiguous()
     nbytes = lib.b200unet_pack_convt_weight_bytes(cin, cout, mode)
-    out = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
+    out = _pack_out(nbytes, w.device, out)
     check(lib.b200unet_pack_convt_weight(w.data_ptr(), cin, cout, mode, out.data_ptr(), stream_ptr()),
           "pack_convt_weight")
     return out
@@ -113,6 +119,8 @@ def conv_fwd(srcs: Sequence[torch.Tensor], w: torch.Tensor, bias: Optional[torch
     p.w_f32, p.bias, p.relu = w.data_ptr(), ptr(bias), int(relu)
     p.dst, p.impl = view(out), impl
     if impl != IMPL_DIRECT and lib.b200unet_conv_fwd_impl(C.byref(p)) == IMPL_UMMA:
+        if callable(w_packed):
+            w_packed = w_packed()
         if w_packed is None:
             w_packed = pack_conv_weight(w, [s.shape[3] for s in srcs], 2 if split else 0)
         p.w_packed = w_packed.data_ptr()
@@ -137,6 +145,8 @@ def conv_dgrad(dz: torch.Tensor, w: torch.Tensor, pad: int, dsts: Sequence[torch
         p.mask[i] = ptr(m)
     p.num_dst, p.impl = len(dsts), impl
     if impl != IMPL_DIRECT and lib.b200unet_conv_dgrad_impl(C.byref(p)) == IMPL_UMMA:
+        if callable(w_packed):
+            w_packed = w_packed()
         if w_packed is None:
             w_packed = pack_conv_weight(w, [w.shape[1]], 1)
         p.w_packed = w_packed.data_ptr()
@@ -178,6 +188,8 @@ def convt_fwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], w_
     p.x, p.y = view(x), view(out)
     p.w_f32, p.bias, p.impl = w.data_ptr(), ptr(bias), impl
     if impl != IMPL_DIRECT and lib.b200unet_convt_fwd_impl(C.byref(p)) == IMPL_UMMA:
+        if callable(w_packed):
+            w_packed = w_packed()
         if w_packed is None:
             w_packed = pack_convt_weight(w, 2 if split else 0)
         p.w_packed = w_packed.data_ptr()
@@ -192,6 +204,8 @@ def convt_dgrad(dy: torch.Tensor, w: torch.Tensor, dx: torch.Tensor, mask: Optio
     p.dy, p.dx = view(dy), view(dx)
     p.w_f32, p.mask, p.impl = w.data_ptr(), ptr(mask), impl
     if impl != IMPL_DIRECT and lib.b200unet_convt_dgrad_impl(C.byref(p)) == IMPL_UMMA:
+        if callable(w_packed):
+            w_packed = w_packed()
         if w_packed is None:
             w_packed = pack_convt_weight(w, 1)
         p.w_packed = w_packed.data_ptr()

@@ -177,9 +177,19 @@ class UNet(nn.Module):
         self._grad_alloc: Optional[Callable[[str, Tuple[int, ...], torch.device], torch.Tensor]] = None
         self._grad_ready: Optional[Callable[[str], None]] = None
         self._grads_done: Optional[Callable[[], None]] = None
-        self._pack_cache: Dict[Tuple[str, int], Tuple[int, int, torch.Tensor]] = {}
+        self._pack_cache: Dict[Tuple[str, int], dict] = {}
 
     # ---------------------------------------------------------------- public API
+    def invalidate_packs(self) -> None:
+        """Drop the bf16 operand copies `FusedAdam` maintains.  They are trusted while the parameter keeps its storage
+        and autograd version; call this after modifying weights in a way that bumps neither (writes through `.data`,
+        custom kernels) while training with FusedAdam."""
+        self._pack_cache.clear()
+
+    def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() / .float(): parameters move, copies are stale
+        self._pack_cache.clear()
+        return super()._apply(fn, *args, **kwargs)
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return self._apply_fn(x, None)
 
@@ -282,15 +292,27 @@ class UNet(nn.Module):
 
     # ---------------------------------------------------------------- helpers
     def _packed(self, name: str, w: torch.Tensor, mode: int, src_c=None, transposed_conv: bool = False) -> torch.Tensor:
+        """Packed bf16 operand copy of weight `name` (mode: 0 forward, 1 backward-data, 2 forward of the split tier).
+        The buffer of a (name, mode) entry is persistent — a repack writes into it — so that `FusedAdam` can rewrite
+        it inside its own kernel.  An entry is REUSED without repacking only if FusedAdam stamped it after its last
+        update and the parameter still has that storage and autograd version; with any other optimizer every call
+        repacks (torch's own fused Adam, for one, updates parameters without bumping their version, so a cache keyed
+        on versions alone would serve stale weights).  Internally padded parameters are fresh copies per call."""
+        if name in self._padspec:
+            return (ops.pack_convt_weight(w.detach(), mode) if transposed_conv
+                    else ops.pack_conv_weight(w.detach(), src_c if src_c is not None else [w.shape[1]], mode))
         key = (name, mode)
-        hit = self._pack_cache.get(key)
-        if hit is not None and hit[0] == w._version and hit[1] == w.data_ptr():
-            return hit[2]
+        e = self._pack_cache.get(key)
+        if e is not None and e["stamped"] and e["version"] == w._version and e["ptr"] == w.data_ptr():
+            return e["tensor"]
+        out = e["tensor"] if e is not None and e["tensor"].device == w.device else None
         if transposed_conv:
-            packed = ops.pack_convt_weight(w.detach(), mode)
+            packed = ops.pack_convt_weight(w.detach(), mode, out=out)
         else:
-            packed = ops.pack_conv_weight(w.detach(), src_c if src_c is not None else [w.shape[1]], mode)
-        self._pack_cache[key] = (w._version, w.data_ptr(), packed)
+            src_c = list(src_c) if src_c is not None else [w.shape[1]]
+            packed = ops.pack_conv_weight(w.detach(), src_c, mode, out=out)
+        self._pack_cache[key] = {"version": w._version, "ptr": w.data_ptr(), "tensor": packed, "mode": mode,
+                                 "src_c": src_c, "transposed": transposed_conv, "stamped": False}
         return packed
 
     def _new_grad(self, name: str, like: torch.Tensor) -> torch.Tensor:
@@ -318,7 +340,9 @@ class UNet(nn.Module):
     # ---------------------------------------------------------------- forward
     def _conv(self, name, srcs, P, pad, relu=True):
         w, b = P[name + ".weight"], P[name + ".bias"]
-        return ops.conv_fwd(srcs, w.detach(), b.detach(), pad, relu, impl=self.conv_impl)
+        mode = 2 if isinstance(srcs[0], ops.Split) else 0
+        return ops.conv_fwd(srcs, w.detach(), b.detach(), pad, relu, impl=self.conv_impl,
+                            w_packed=lambda: self._packed(name + ".weight", w, mode, [s.shape[3] for s in srcs]))
 
     def _first_layer_patches(self, prefix: str, srcs, w) -> bool:
         return (prefix == "down_path.0" and self.conv_impl == ops.IMPL_AUTO and len(srcs) == 1
@@ -386,7 +410,9 @@ class UNet(nn.Module):
             rec = {"x": ops.hi_of(cur), "x_act": last_act}
             if self.up_mode == "upconv":
                 w, b = P[f"up_path.{j}.up.weight"].detach(), P[f"up_path.{j}.up.bias"].detach()
-                upv = ops.convt_fwd(cur, w, b, impl=self.conv_impl)
+                wname, wparam, mode = f"up_path.{j}.up.weight", P[f"up_path.{j}.up.weight"], 2 if isinstance(cur, ops.Split) else 0
+                upv = ops.convt_fwd(cur, w, b, impl=self.conv_impl,
+                                    w_packed=lambda: self._packed(wname, wparam, mode, transposed_conv=True))
             else:
                 u = ops.bilinear_fwd(cur)
                 rec["u"] = ops.hi_of(u)
@@ -445,9 +471,11 @@ class UNet(nn.Module):
             grads[names[i] + ".weight"], grads[names[i] + ".bias"] = dw, db
             if i == 1:
                 g = torch.empty_like(rec["o0"])
-                ops.conv_dgrad(dz, w.detach(), pad, [g], [None if blk.batch_norm else rec["a0"]], impl=self.conv_impl)
+                ops.conv_dgrad(dz, w.detach(), pad, [g], [None if blk.batch_norm else rec["a0"]], impl=self.conv_impl,
+                               w_packed=lambda: self._packed(names[i] + ".weight", w, 1))
             elif src_dsts is not None:
-                ops.conv_dgrad(dz, w.detach(), pad, src_dsts, src_masks, impl=self.conv_impl)
+                ops.conv_dgrad(dz, w.detach(), pad, src_dsts, src_masks, impl=self.conv_impl,
+                               w_packed=lambda: self._packed(names[i] + ".weight", w, 1))
             self._done(*( [bn_names[i] + ".weight", bn_names[i] + ".bias"] if blk.batch_norm else [] ),
                        names[i] + ".weight", names[i] + ".bias")
 
@@ -494,7 +522,8 @@ class UNet(nn.Module):
                 dw = self._new_grad(wn + ".weight", w)
                 db = self._new_grad(wn + ".bias", P[wn + ".bias"])
                 ops.convt_wgrad(xin, d_up, impl=self.conv_impl, dw=dw, db=db)
-                ops.convt_dgrad(d_up, w.detach(), g, mask=xmask, impl=self.conv_impl)
+                ops.convt_dgrad(d_up, w.detach(), g, mask=xmask, impl=self.conv_impl,
+                                w_packed=lambda: self._packed(wn + ".weight", w, 1, transposed_conv=True))
             else:
                 wn = f"up_path.{j}.up.1"
                 w = P[wn + ".weight"]
@@ -502,7 +531,8 @@ class UNet(nn.Module):
                 db = self._new_grad(wn + ".bias", P[wn + ".bias"])
                 ops.conv_wgrad(d_up, [rec["u"]], 1, 0, impl=self.conv_impl, dw=dw, db=db)
                 gu = torch.empty_like(rec["u"])
-                ops.conv_dgrad(d_up, w.detach(), 0, [gu], [None], impl=self.conv_impl)
+                ops.conv_dgrad(d_up, w.detach(), 0, [gu], [None], impl=self.conv_impl,
+                               w_packed=lambda: self._packed(wn + ".weight", w, 1))
                 ops.bilinear_bwd(gu, g, mask=xmask)
             grads[wn + ".weight"], grads[wn + ".bias"] = dw, db
             self._done(wn + ".weight", wn + ".bias")

@@ -1,0 +1,154 @@
+"""FusedAdam: one launch = torch.optim.Adam's update for every parameter + refresh of the
+packed bf16 operand copies.  Checked against torch.optim.Adam itself (the reference's optimizer, README.md:49 /
+run.py:71), against the stand-alone pack kernels (bit-exact), and through state_dict round trips in both directions."""
+import copy
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gpu_util import rel_l2
+from oracle import unet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def test_matches_torch_adam_on_plain_tensors():
+    from b200unet import FusedAdam
+    torch.manual_seed(0)
+    shapes = [(7,), (64,), (3, 5), (2048,), (2049,), (33, 17, 3, 3), (100000,)]
+    ps = [torch.randn(s, device="cuda").requires_grad_(True) for s in shapes]
+    qs = [p.detach().clone().requires_grad_(True) for p in ps]
+    a = FusedAdam(ps, lr=1e-2, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-2)
+    b = torch.optim.Adam(qs, lr=1e-2, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-2)
+    for it in range(6):
+        if it == 3:  # LR decay between steps (run.py:358-363)
+            for opt in (a, b):
+                for g in opt.param_groups:
+                    g["lr"] *= 0.5
+        for p, q in zip(ps, qs):
+            g = torch.randn_like(p)
+            p.grad, q.grad = g.clone(), g.clone()
+        a.step()
+        b.step()
+    for p, q in zip(ps, qs):
+        # same formulas as torch's fused kernel; differences are FMA-contraction ulps
+        assert torch.allclose(p, q, rtol=2e-6, atol=1e-6)
+        assert torch.allclose(a.state[p]["exp_avg"], b.state[q]["exp_avg"], rtol=1e-5, atol=1e-6)
+        assert torch.allclose(a.state[p]["exp_avg_sq"], b.state[q]["exp_avg_sq"], rtol=1e-5, atol=1e-7)
+        assert float(a.state[p]["step"]) == 6.0 == float(b.state[q]["step"])
+
+
+CASES = {
+    "paper_valid_upconv": O.UNetSpec(1, 2, 3, 5, False, False, "upconv"),
+    "paper_same_bn_upsample_split": O.UNetSpec(1, 2, 3, 5, True, True, "upsample"),
+    "deep_narrow_padded": O.UNetSpec(3, 4, 3, 2, True, True, "upsample", True, "deep"),
+}
+
+
+def _build(spec):
+    import b200unet
+    return b200unet.UNet(spec.in_channels, spec.n_classes, spec.depth, spec.wf, spec.padding, spec.batch_norm,
+                         spec.up_mode, spec.non_neg, up_block=spec.up_block).cuda().train()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_training_matches_torch_adam_and_packs_are_exact(name):
+    from b200unet import FusedAdam, ops, load_library
+    spec = CASES[name]
+    torch.manual_seed(1)
+    m1 = _build(spec)
+    m2 = copy.deepcopy(m1)
+    o1 = FusedAdam(m1.parameters(), lr=1e-3, model=m1)
+    o2 = torch.optim.Adam(m2.parameters(), lr=1e-3)
+    x = torch.randn(2, spec.in_channels, 44, 60, device="cuda")
+    ho, wo = O.output_hw(spec, 44, 60)
+    y = torch.randint(0, spec.n_classes, (2, ho, wo), device="cuda")
+    lib = load_library()
+    launches = []
+    for it in range(4):
+        l0 = lib.b200unet_launch_count()
+        loss1 = m1.loss(x, y)
+        o1.zero_grad(set_to_none=True)
+        loss1.backward()
+        o1.step()
+        launches.append(lib.b200unet_launch_count() - l0)
+        loss2 = m2.loss(x, y)
+        o2.zero_grad(set_to_none=True)
+        loss2.backward()
+        o2.step()
+        assert abs(float(loss1) - float(loss2)) <= 2e-3 * max(1.0, abs(float(loss2))), (it, float(loss1), float(loss2))
+    w1 = torch.cat([p.detach().flatten() for p in m1.parameters()])
+    w2 = torch.cat([p.detach().flatten() for p in m2.parameters()])
+    assert rel_l2(w1, w2) < 2e-3  # identical updates up to the bf16 forward's sensitivity to 1-ulp weight differences
+    # the operand copies the fused kernel maintains are bit-identical to what the pack kernels produce from the weights
+    params = dict(m1.named_parameters())
+    n_fused = 0
+    for (pname, mode), e in m1._pack_cache.items():
+        w = params[pname].detach()
+        assert e["version"] == params[pname]._version and e["ptr"] == w.data_ptr(), (pname, mode)
+        fresh = ops.pack_convt_weight(w, mode) if e["transposed"] else ops.pack_conv_weight(w, e["src_c"], mode)
+        assert torch.equal(e["tensor"], fresh), (pname, mode)
+        n_fused += 1
+    if not m1._padspec:
+        assert n_fused > 0
+        # steady state: no pack launches any more (first step packs, later steps do not)
+        assert launches[-1] < launches[0] - n_fused + 2, launches
+
+
+def test_state_dict_round_trips_with_torch_adam():
+    from b200unet import FusedAdam
+    spec = CASES["paper_valid_upconv"]
+    torch.manual_seed(2)
+    m1 = _build(spec)
+    x = torch.randn(1, 1, 44, 44, device="cuda")
+    ho, wo = O.output_hw(spec, 44, 44)
+    y = torch.randint(0, 2, (1, ho, wo), device="cuda")
+
+    def run(model, opt, n):
+        for _ in range(n):
+            loss = model.loss(x, y)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+
+    o1 = FusedAdam(m1.parameters(), lr=1e-3, model=m1)
+    run(m1, o1, 2)
+    # FusedAdam -> torch.optim.Adam
+    m2 = copy.deepcopy(m1)
+    o2 = torch.optim.Adam(m2.parameters(), lr=1e-3)
+    o2.load_state_dict(copy.deepcopy(o1.state_dict()))
+    assert all(float(s["step"]) == 2.0 for s in o2.state.values())
+    # torch.optim.Adam -> FusedAdam (checkpoint written by the reference's trainer, run.py:428)
+    m3 = copy.deepcopy(m1)
+    o3 = FusedAdam(m3.parameters(), lr=1e-3, model=m3)
+    o3.load_state_dict(copy.deepcopy(o2.state_dict()))
+    run(m1, o1, 2)
+    run(m2, o2, 2)
+    run(m3, o3, 2)
+    w1, w2, w3 = (torch.cat([p.detach().flatten() for p in m.parameters()]) for m in (m1, m2, m3))
+    assert rel_l2(w3, w1) < 1e-6      # same optimizer resumed from the checkpoint: same trajectory
+    assert rel_l2(w2, w1) < 2e-3
+    assert float(next(iter(o3.state.values()))["step"]) == 4.0
+
+
+def test_cuda_graph_step_with_fused_adam():
+    import b200unet
+    spec = CASES["paper_same_bn_upsample_split"]
+    torch.manual_seed(3)
+    m1 = _build(spec)
+    m2 = copy.deepcopy(m1)
+    x = torch.randn(2, 1, 32, 32, device="cuda")
+    y = torch.randint(0, 2, (2, 32, 32), device="cuda")
+    o2 = b200unet.FusedAdam(m2.parameters(), lr=1e-3, model=m2)
+    eager = []
+    for _ in range(6):
+        loss = m2.loss(x, y)
+        o2.zero_grad(set_to_none=True)
+        loss.backward()
+        o2.step()
+        eager.append(float(loss))
+    step = b200unet.GraphedTrainStep(m1, b200unet.FusedAdam(m1.parameters(), lr=1e-3, model=m1), x, y, warmup=3)
+    graphed = [float(step(x, y)) for _ in range(3)]   # warm-up ran steps 0..2, the capture itself does not execute
+    for a, b in zip(graphed, eager[3:]):
+        assert abs(a - b) <= 2e-3 * max(1.0, abs(b)), (graphed, eager)
