@@ -14,7 +14,7 @@ namespace b200 {
 constexpr int kScThreads = 256;
 
 template <int CIN>
-__global__ void __launch_bounds__(kScThreads)
+__global__ void __launch_bounds__(kScThreads, 2)
 smallc_fwd_kernel(DView src, DView dst, const float* __restrict__ w, const float* __restrict__ bias, int relu, int pad) {
   __shared__ __align__(16) float ws[9 * CIN * 64];
   __shared__ float bs[64];
@@ -31,8 +31,12 @@ smallc_fwd_kernel(DView src, DView dst, const float* __restrict__ w, const float
   const int q4 = threadIdx.x & 3;
   const int groups_per_row = (dst.w + 3) >> 2;
   const long long total_groups = (long long)dst.n * dst.h * groups_per_row;
-  const long long pg = (long long)blockIdx.x * (kScThreads / 4) + (threadIdx.x >> 2);
-  if (pg >= total_groups || o_base + q4 * 16 >= cout) return;
+  if (o_base + q4 * 16 >= cout) return;
+  // grid-stride over pixel groups: the weights are staged once per block (one block per 256 pixels spent more time in
+  // its prologue and in block scheduling than in the 576 FMAs per thread)
+  for (long long pg = (long long)blockIdx.x * (kScThreads / 4) + (threadIdx.x >> 2); pg < total_groups;
+       pg += (long long)gridDim.x * (kScThreads / 4)) {
+  asm volatile("" ::: "memory");  // keep the weight LDS inside the iteration (hoisted, 9*CIN*16 values spill)
   const int xg = (int)(pg % groups_per_row);
   const long long t2 = pg / groups_per_row;
   const int oy = (int)(t2 % dst.h), n = (int)(t2 / dst.h);
@@ -98,6 +102,7 @@ smallc_fwd_kernel(DView src, DView dst, const float* __restrict__ w, const float
     }
     store8s(dst.p, dst.lo, oo, f0);
     store8s(dst.p, dst.lo, oo + 8, f1);
+  }
   }
 }
 
@@ -260,7 +265,9 @@ bool smallc_conv_fwd_ok(const b200_conv_fwd_params* p) {
 
 int smallc_conv_fwd(const b200_conv_fwd_params* p, cudaStream_t st) {
   const long long groups = (long long)p->dst.n * p->dst.h * ((p->dst.w + 3) / 4);
-  dim3 grid((unsigned)((groups + kScThreads / 4 - 1) / (kScThreads / 4)), (unsigned)((p->dst.c + 63) / 64));
+  long long gx = (groups + kScThreads / 4 - 1) / (kScThreads / 4);
+  if (gx > 8 * kNumSMsB200) gx = 8 * kNumSMsB200;
+  dim3 grid((unsigned)gx, (unsigned)((p->dst.c + 63) / 64));
   const DView s = dview(p->src[0]), d = dview(p->dst);
   switch (p->src[0].c) {
     case 1: smallc_fwd_kernel<1><<<grid, kScThreads, 0, st>>>(s, d, p->w_f32, p->bias, p->relu, p->pad); break;

@@ -323,29 +323,60 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
-// dw[(m * n_total + n) * taps + tap] = sum_s ws[s][tap][m][npad(n)].  Block = one m, 32 consecutive n, all taps: reads
-// are coalesced along n, the transposed result goes through shared memory so that the store is contiguous.
-__global__ void wgrad_umma_reduce_kernel(const float* __restrict__ ws, int splits, int taps, int m_total, int n_total,
-                                         int m_pad, int n_pad, int c_src0, int n_blks0, float* __restrict__ dw,
-                                         const float* __restrict__ ws_bias, float* __restrict__ db) {
-  __shared__ float tile[32 * 9];
+// dw[(m * n_total + n) * taps + tap] = sum_s ws[s][tap][m][npad(n)].  Block = one m, 128 consecutive n, all taps (one
+// warp per tap, one float4 = 4 consecutive n per lane): 512-byte coalesced reads with the split loop unrolled so that
+// eight loads are in flight per thread, and the transposed result goes through shared memory so that the store is
+// contiguous.  (The first version — 32 n per block, scalar loads, one dependent load per iteration — ran at a third
+// of the HBM rate and cost ~1 ms per training step.)  Summation order over the splits is fixed: reproducible.
+constexpr int kRedN = 128;
+__global__ void __launch_bounds__(32 * 9)
+wgrad_umma_reduce_kernel(const float* __restrict__ ws, int splits, int taps, int m_total, int n_total, int m_pad,
+                         int n_pad, int c_src0, int n_blks0, float* __restrict__ dw,
+                         const float* __restrict__ ws_bias, float* __restrict__ db) {
+  __shared__ float tile[kRedN * 9];
   const int m = blockIdx.y;
-  const int n0 = blockIdx.x * 32;
-  const int nl = threadIdx.x & 31, t = threadIdx.x >> 5;
-  const int n = n0 + nl;
+  const int n0 = blockIdx.x * kRedN;
+  const int lane = threadIdx.x & 31, t = threadIdx.x >> 5;
+  const int n = n0 + 4 * lane;  // channel counts are multiples of 8: the four n of a lane belong to the same source
   if (t < taps && n < n_total) {
     const int np = n < c_src0 ? n : n_blks0 + (n - c_src0);  // n_blks0 = padded width of source 0 here
-    float s = 0.f;
-    for (int i = 0; i < splits; ++i) s += ws[(((long long)i * taps + t) * m_pad + m) * n_pad + np];
-    tile[nl * taps + t] = s;
+    const long long stride = (long long)taps * m_pad * n_pad;
+    const float* p = ws + ((long long)t * m_pad + m) * n_pad + np;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    int i = 0;
+    for (; i + 8 <= splits; i += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const float4*>(p + (i + u) * stride);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        s.x += v[u].x;
+        s.y += v[u].y;
+        s.z += v[u].z;
+        s.w += v[u].w;
+      }
+    }
+    for (; i < splits; ++i) {
+      const float4 v = *reinterpret_cast<const float4*>(p + i * stride);
+      s.x += v.x;
+      s.y += v.y;
+      s.z += v.z;
+      s.w += v.w;
+    }
+    const int nl = 4 * lane;
+    tile[(nl + 0) * taps + t] = s.x;
+    tile[(nl + 1) * taps + t] = s.y;
+    tile[(nl + 2) * taps + t] = s.z;
+    tile[(nl + 3) * taps + t] = s.w;
   }
   __syncthreads();
-  const int cnt = min(32, n_total - n0) * taps;
+  const int cnt = min(kRedN, n_total - n0) * taps;
   for (int j = threadIdx.x; j < cnt; j += blockDim.x) dw[((long long)m * n_total + n0) * taps + j] = tile[j];
-  if (db && blockIdx.x == 0 && threadIdx.x == 0) {
+  if (db && blockIdx.x == 0 && t == 0) {  // bias gradient: lanes stride over the splits, fixed butterfly
     float s = 0.f;
-    for (int i = 0; i < splits; ++i) s += ws_bias[(long long)i * m_pad + m];
-    db[m] = s;
+    for (int i = lane; i < splits; i += 32) s += ws_bias[(long long)i * m_pad + m];
+    s = warp_sum(s);
+    if (lane == 0) db[m] = s;
   }
 }
 
@@ -510,8 +541,8 @@ static int wg_launch(const WgMaps& maps, WgPlan& pl, float* dw, float* db, int c
   wgrad_umma_kernel<<<pl.grid, kWgThreads, pl.smem_bytes, st>>>(maps, pl.a);
   int r = check_launch("wgrad_umma");
   if (r) return r;
-  dim3 grid((unsigned)((pl.a.n_total + 31) / 32), (unsigned)pl.a.m_total);
-  wgrad_umma_reduce_kernel<<<grid, 32 * 9, 0, st>>>(pl.a.ws, pl.a.splits, pl.a.taps, pl.a.m_total, pl.a.n_total,
+  dim3 grid((unsigned)((pl.a.n_total + kRedN - 1) / kRedN), (unsigned)pl.a.m_total);
+  wgrad_umma_reduce_kernel<<<grid, 32 * pl.a.taps, 0, st>>>(pl.a.ws, pl.a.splits, pl.a.taps, pl.a.m_total, pl.a.n_total,
                                                    pl.a.m_pad, pl.a.n_pad, c_src0, pl.a.n_blks0 * pl.a.nbw, dw,
                                                    pl.a.bias ? pl.a.ws_bias : nullptr, pl.a.bias ? db : nullptr);
   return check_launch("wgrad_umma_reduce");
