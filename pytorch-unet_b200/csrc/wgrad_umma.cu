@@ -17,6 +17,11 @@
 //     tile stored one pixel row later.  One MMA with gathered shift sigma then yields tap sigma+1 on lanes 0..63 and
 //     tap sigma on lanes 64..127: the nine taps need 6 MMAs (sigma = rP and rP+2) and 384 columns — one pass.
 // Bias gradient: one extra N = 16 MMA per K step against a block of ones (column sums of dz on the tensor core).
+// CTA pairs (cta2 mode, tcgen05 cta_group::2; >= 256 row channels and N = 128): two CTAs take the two 128-channel M
+// blocks of the same (split, N block) and execute ONE MMA of M = 256 per tap and K step; each loads its own R tile and
+// only ONE 64-channel half of the gathered tile (the MMA reads the other half from the peer).  The kernel is fed from L2
+// (~43 B/cycle/SM chip-wide); this cuts its demand from ~47 to ~34 B/cycle per MMA cycle, and a stage shrinks enough
+// for a third pipeline stage.
 // Work item = (pixel split, 64-channel N block, 128-channel M block); fp32 partials [split][tap][M][N] (+ [split][M]
 // for the bias); a second kernel reduces the splits in a fixed order and writes the state_dict layout, so results are
 // run-to-run reproducible.
@@ -58,6 +63,8 @@ struct WgArgs {
   uint32_t r_blk_bytes, g_tile_bytes, g_box_bytes, stage_bytes;
   int stages;
   int r_blocks;  // 64-channel blocks of the row operand actually loaded (1 or 2)
+  int cta2;      // CTA pairs (see header): cluster of 2, rank = parity of the M block
+  int m_units;   // M blocks (cta2: pairs of M blocks) enumerated by the work items
 };
 
 struct WgItem {
@@ -68,10 +75,11 @@ struct WgItem {
 
 // A CTA runs both tap groups of a (split, N block, M block) back to back, so that every CTA gets the same amount of
 // MMA work (5 + 4 taps) and the second pass re-reads tiles that are still warm in L2.
-__device__ __forceinline__ WgItem decode_item(const WgArgs& a, int item, int grp) {
+__device__ __forceinline__ WgItem decode_item(const WgArgs& a, int item, int grp, int rank) {
   WgItem w;
-  w.mb = item % a.m_blks;
-  item /= a.m_blks;
+  w.mb = item % a.m_units;
+  if (a.cta2) w.mb = 2 * w.mb + rank;
+  item /= a.m_units;
   w.nb = item % a.n_blks;
   w.split = item / a.n_blks;
   w.grp = grp;
@@ -89,6 +97,8 @@ __device__ __forceinline__ WgItem decode_item(const WgArgs& a, int item, int grp
   return w;
 }
 
+// CTA2 is a template parameter: a kernel that contains cta_group::2 instructions can only be launched as a cluster.
+template <bool CTA2>
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -102,8 +112,13 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_items = a.m_blks * a.n_blks * a.splits;
+  const int total_items = a.m_units * a.n_blks * a.splits;
   const int g_tiles = a.mode == 1 ? a.taps : 1;
+  const int cl = CTA2 ? 2 : 1;
+  const int rank = CTA2 ? (int)cluster_ctarank() : 0;
+  const int item0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int item_step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int g_sub = (a.nbw / 64) / cl;  // 64-channel sub-tiles of the gathered operand held by THIS CTA (per tap)
 
   // zero the whole pipeline once: halo columns / tail rows of the R tiles and the unused tail of the G tiles must
   // read as 0 (never NaN bit patterns); TMA only ever writes the box interiors afterwards.
@@ -121,13 +136,16 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
       mbar_init(&empty[i], 1);
     }
     mbar_init(t_full, 1);
-    mbar_init(t_empty, 4);
+    mbar_init(t_empty, 4 * cl);  // cta2: the leader's barrier also collects the peer's epilogue warps
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) {
+    if (CTA2) tmem_alloc2<512>(tmem_slot); else tmem_alloc<512>(tmem_slot);
+  }
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
+  if (CTA2) cluster_sync_all();  // the peer's barriers must be initialised before anything arrives on them
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -137,9 +155,9 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
       int stage = 0;
       uint32_t phase = 0;
       const int r_loads = a.paired ? 2 : a.r_blocks;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x)
+      for (int item = item0; item < total_items; item += item_step)
         for (int grp = 0; grp < a.tap_groups; ++grp) {
-          const WgItem w = decode_item(a, item, grp);
+          const WgItem w = decode_item(a, item, grp, rank);
           // gathered-operand source of this N block
           int gsrc = 0, gc0 = w.nb * a.nbw;
           if (a.mode == 0 && w.nb >= a.n_blks0) {
@@ -153,26 +171,30 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
             const int y0 = tyi * a.TH, x0 = txi * a.TW;
             uint8_t* st = smem + stage * a.stage_bytes;
             mbar_wait(&empty[stage], phase ^ 1);
-            const uint32_t tx_bytes = (uint32_t)r_loads * a.TH * a.TW * 128 + (uint32_t)g_tiles * (a.nbw / 64) * a.g_box_bytes;
-            mbar_arrive_expect_tx(&full[stage], tx_bytes);
+            const uint32_t tx_bytes = (uint32_t)r_loads * a.TH * a.TW * 128 + (uint32_t)g_tiles * g_sub * a.g_box_bytes;
+            // cta2: the loads of both CTAs complete on the leader's barrier
+            if (rank == 0) mbar_arrive_expect_tx(&full[stage], cl * tx_bytes);
+            auto load = [&](const CUtensorMap* m, void* dst, int c0, int c1, int c2, int c3) {
+              if (CTA2) tma_load_4d_2cta(m, &full[stage], dst, c0, c1, c2, c3);
+              else tma_load_4d(m, &full[stage], dst, c0, c1, c2, c3);
+            };
             // R tile: one TMA per tile row so that rows land with pitch P (halo columns stay zero).  Paired mode:
             // block 0 holds the tile one row later (row q+1 = pixel q), block 1 holds it in place.
             for (int rb = 0; rb < r_loads; ++rb) {
               const int ch = a.paired ? w.mb * 128 : w.mb * 128 + rb * 64;
               const int row_off = (a.paired && rb == 0) ? 1 : 0;
               for (int ty = 0; ty < a.TH; ++ty)
-                tma_load_4d(&maps.r, &full[stage], st + rb * a.r_blk_bytes + (uint32_t)(ty * a.P + row_off) * 128, ch, x0,
-                            y0 + ty, n);
+                load(&maps.r, st + rb * a.r_blk_bytes + (uint32_t)(ty * a.P + row_off) * 128, ch, x0, y0 + ty, n);
             }
             uint8_t* gt = st + 2 * a.r_blk_bytes;
+            // gathered operand: this CTA's 64-channel sub-tiles (cta2: sub-tile `rank` of the two)
             if (a.mode == 0) {
-              tma_load_4d(&maps.g[gsrc], &full[stage], gt, gc0, x0 - a.pad, y0 - a.pad, n);
-              if (a.nbw == 128)
-                tma_load_4d(&maps.g[gsrc], &full[stage], gt + a.g_tile_bytes, gc0 + 64, x0 - a.pad, y0 - a.pad, n);
+              for (int h = 0; h < g_sub; ++h)
+                load(&maps.g[gsrc], gt + h * a.g_tile_bytes, gc0 + (rank * g_sub + h) * 64, x0 - a.pad, y0 - a.pad, n);
             } else {
               for (int t = 0; t < a.taps; ++t)
-                for (int h = 0; h < a.nbw / 64; ++h)
-                  tma_load_4d(&maps.g[t], &full[stage], gt + (t * (a.nbw / 64) + h) * a.g_tile_bytes, gc0 + h * 64, x0, y0, n);
+                for (int h = 0; h < g_sub; ++h)
+                  load(&maps.g[t], gt + (t * g_sub + h) * a.g_tile_bytes, gc0 + (rank * g_sub + h) * 64, x0, y0, n);
             }
             if (++stage == a.stages) {
               stage = 0;
@@ -184,8 +206,8 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
   } else if (warp == 1) {
     // The whole warp runs the control flow so that every address / descriptor is warp-uniform (lives in uniform
     // registers, no per-MMA R2UR/ELECT sequences); one elected lane issues the tcgen05 instructions.
-    const uint32_t idesc = umma_idesc_bf16(128, a.nbw, 1, 1);  // both operands MN-major
-    constexpr uint32_t idesc_bias = umma_idesc_bf16(128, 16, 1, 1);
+    const uint32_t idesc = umma_idesc_bf16(128 * cl, a.nbw, 1, 1);  // both operands MN-major
+    const uint32_t idesc_bias = umma_idesc_bf16(128 * cl, 16, 1, 1);
     const uint64_t hi_r = umma_desc_hi_sw128(a.r_blk_bytes, 1024);
     const uint64_t hi_g = umma_desc_hi_sw128(a.g_tile_bytes, 1024);  // LBO = distance of the second 64-channel sub-tile
     const uint64_t ones_desc = umma_desc(umma_desc_hi_sw128(a.r_blk_bytes, 1024), smem_u32(ones));
@@ -196,9 +218,10 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
     const int nbw = a.nbw;
     const uint32_t stage_bytes = a.stage_bytes, r_blk_bytes = a.r_blk_bytes;
     const int n_stages = a.stages;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x)
+    // cta2: the leader issues for the pair; the peer's warp only took part in the TMEM allocation
+    for (int item = (CTA2 && rank != 0) ? total_items : item0; item < total_items; item += item_step)
       for (int grp = 0; grp < a.tap_groups; ++grp, ++it) {
-        const WgItem w = decode_item(a, item, grp);
+        const WgItem w = decode_item(a, item, grp, rank);
         const bool do_bias = a.bias && w.nb == 0 && grp == 0;
         // per-item table of gathered-operand start offsets (in descriptor units of 16 B): no division / constant
         // loads inside the issue loop — with N = 64 MMAs (48 cycles each) the issuing lane is otherwise the bottleneck
@@ -214,7 +237,7 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
               const int r = tap / a.kx, sx = tap - r * a.kx;
               o = (uint32_t)(r * a.P + sx) * 8;
             } else {
-              o = (uint32_t)(w.tap0 + j) * (a.nbw / 64) * (a.g_tile_bytes >> 4);
+              o = (uint32_t)(w.tap0 + j) * g_sub * (a.g_tile_bytes >> 4);
             }
           }
           goff[j] = o;
@@ -230,24 +253,45 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
           const uint64_t r_desc = umma_desc(hi_r, r_base);
           const uint64_t g_desc0 = umma_desc(hi_g, r_base + 2 * r_blk_bytes);
           if (elect_one()) {
+            if (CTA2) {
 #pragma unroll
-            for (int j = 0; j < 6; ++j) {
-              if (j < ntap) {
-                const uint64_t g_desc = g_desc0 + goff[j];
-                const uint32_t d = tmem_base + j * nbw;
-                // one K step = 16 pixel rows = 2048 B = 128 in the descriptor's (address >> 4) field
-                umma_bf16(d, r_desc, g_desc, idesc, accum);
+              for (int j = 0; j < 6; ++j) {
+                if (j < ntap) {
+                  const uint64_t g_desc = g_desc0 + goff[j];
+                  const uint32_t d = tmem_base + j * nbw;
+                  umma_bf16_2cta(d, r_desc, g_desc, idesc, accum);
 #pragma unroll 4
-                for (int k = 1; k < ksteps; ++k) umma_bf16(d, r_desc + (uint64_t)k * 128, g_desc + (uint64_t)k * 128, idesc, 1u);
+                  for (int k = 1; k < ksteps; ++k)
+                    umma_bf16_2cta(d, r_desc + (uint64_t)k * 128, g_desc + (uint64_t)k * 128, idesc, 1u);
+                }
               }
-            }
-            if (do_bias) {
-              umma_bf16(tmem_base + kWgBiasCol, r_desc, ones_desc, idesc_bias, accum);
+              if (do_bias) {
+                umma_bf16_2cta(tmem_base + kWgBiasCol, r_desc, ones_desc, idesc_bias, accum);
 #pragma unroll 4
-              for (int k = 1; k < ksteps; ++k)
-                umma_bf16(tmem_base + kWgBiasCol, r_desc + (uint64_t)k * 128, ones_desc, idesc_bias, 1u);
+                for (int k = 1; k < ksteps; ++k)
+                  umma_bf16_2cta(tmem_base + kWgBiasCol, r_desc + (uint64_t)k * 128, ones_desc, idesc_bias, 1u);
+              }
+              umma_commit_2cta(&empty[stage], (uint16_t)0x3);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 6; ++j) {
+                if (j < ntap) {
+                  const uint64_t g_desc = g_desc0 + goff[j];
+                  const uint32_t d = tmem_base + j * nbw;
+                  // one K step = 16 pixel rows = 2048 B = 128 in the descriptor's (address >> 4) field
+                  umma_bf16(d, r_desc, g_desc, idesc, accum);
+#pragma unroll 4
+                  for (int k = 1; k < ksteps; ++k) umma_bf16(d, r_desc + (uint64_t)k * 128, g_desc + (uint64_t)k * 128, idesc, 1u);
+                }
+              }
+              if (do_bias) {
+                umma_bf16(tmem_base + kWgBiasCol, r_desc, ones_desc, idesc_bias, accum);
+#pragma unroll 4
+                for (int k = 1; k < ksteps; ++k)
+                  umma_bf16(tmem_base + kWgBiasCol, r_desc + (uint64_t)k * 128, ones_desc, idesc_bias, 1u);
+              }
+              umma_commit(&empty[stage]);
             }
-            umma_commit(&empty[stage]);
           }
           __syncwarp();
           accum = 1;
@@ -256,16 +300,18 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
             phase ^= 1;
           }
         }
-        if (elect_one()) umma_commit(t_full);
+        if (elect_one()) {
+          if (CTA2) umma_commit_2cta(t_full, (uint16_t)0x3); else umma_commit(t_full);
+        }
         __syncwarp();
       }
   } else {
     // epilogue: TMEM -> fp32 partials ws[split][tap][m][n]
     const int quarter = warp & 3;
     int it = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x)
+    for (int item = item0; item < total_items; item += item_step)
       for (int grp = 0; grp < a.tap_groups; ++grp, ++it) {
-        const WgItem w = decode_item(a, item, grp);
+        const WgItem w = decode_item(a, item, grp, rank);
         mbar_wait(t_full, it & 1);
         tc_fence_after_sync();
         const int row = quarter * 32 + lane;           // TMEM lane = accumulator row
@@ -315,12 +361,17 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
         }
         tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(t_empty);
+        if (lane == 0) {
+          if (CTA2) mbar_arrive_cluster(t_empty, 0); else mbar_arrive(t_empty);
+        }
       }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
+  if (CTA2) cluster_sync_all();  // the pair's MMAs read this CTA's shared memory and arrive on its barriers
+  if (warp == 1) {
+    if (CTA2) tmem_dealloc2<512>(tmem_base); else tmem_dealloc<512>(tmem_base);
+  }
 }
 
 // dw[(m * n_total + n) * taps + tap] = sum_s ws[s][tap][m][npad(n)].  Block = one m, 128 consecutive n, all taps (one
@@ -388,6 +439,7 @@ wgrad_umma_reduce_kernel(const float* __restrict__ ws, int splits, int taps, int
 // B200UNET_WGRAD_N64=1 / B200UNET_WGRAD_MIN_STAGES=k override for experiments.
 static int g_wgrad_n128 = getenv("B200UNET_WGRAD_N64") ? 0 : 1;
 static int g_wgrad_min_stages = getenv("B200UNET_WGRAD_MIN_STAGES") ? atoi(getenv("B200UNET_WGRAD_MIN_STAGES")) : 2;
+static int g_wgrad_cta2 = getenv("B200UNET_WGRAD_NO_PAIRS") ? 0 : 1;
 
 struct WgPlan {
   WgArgs a;
@@ -443,7 +495,11 @@ static bool wg_make_plan(int mode, int Ho, int Wo, int n_img, int m_total, int n
   a.tap_groups = (taps == 9 && !a.paired) ? (a.nbw == 128 ? 3 : 2) : 1;
   a.m_pad = a.m_blks * 128;
   a.n_pad = a.n_blks * a.nbw;
-  const int g_tiles = (mode == 1 ? taps : 1) * (a.nbw / 64);
+  // CTA pairs (cta_group::2): two M blocks per work item, each CTA loads one of the two 64-channel gathered sub-tiles
+  a.cta2 = (g_wgrad_cta2 && a.nbw == 128 && !a.paired && a.m_blks % 2 == 0 && m_total % 128 == 0) ? 1 : 0;
+  a.m_units = a.cta2 ? a.m_blks / 2 : a.m_blks;
+  const int cl = a.cta2 ? 2 : 1;
+  const int g_tiles = (mode == 1 ? taps : 1) * (a.nbw / 64) / cl;  // gathered sub-tiles per CTA and stage
   const int r_loads = a.paired ? 2 : a.r_blocks;
   const double mma_groups = a.paired ? 6.0 : (taps == 9 ? (a.nbw == 128 ? 3.0 : 4.5) : (double)taps);
   const double mma_cycles = a.nbw == 128 ? 64.0 : 48.0;
@@ -489,17 +545,18 @@ static bool wg_make_plan(int mode, int Ho, int Wo, int n_img, int m_total, int n
   if (stages > kWgMaxStages) stages = kWgMaxStages;
   a.stages = stages;
   const long long tiles = (long long)a.tiles_x * a.tiles_y * n_img;
-  const long long base_items = (long long)a.m_blks * a.n_blks;
+  const long long base_items = (long long)a.m_units * a.n_blks;
+  const int slots = wg_sms() / cl;  // work items resident at a time (cta2: CTA pairs)
   // pixel splits: make the number of work items fill whole waves of the persistent grid
   long long splits = 1;
   double best_eff = 0.0;
   for (int k = 1; k <= 3; ++k) {
-    long long sp = (long long)wg_sms() * k / base_items;
+    long long sp = (long long)slots * k / base_items;
     if (sp < 1) sp = 1;
     if (sp > tiles) sp = tiles;
     const long long items = base_items * sp;
-    const long long waves = (items + wg_sms() - 1) / wg_sms();
-    const double eff = (double)items / (double)(waves * wg_sms());
+    const long long waves = (items + slots - 1) / slots;
+    const double eff = (double)items / (double)(waves * slots);
     if (eff > best_eff + 0.03) {
       best_eff = eff;
       splits = sp;
@@ -513,7 +570,7 @@ static bool wg_make_plan(int mode, int Ho, int Wo, int n_img, int m_total, int n
   pl->ws_bias_bytes = a.bias ? (size_t)splits * a.m_pad * 4 : 0;
   pl->smem_bytes = (uint32_t)a.stages * a.stage_bytes + kWgOnesBytes + 1024 + 256;
   const long long items = base_items * splits;
-  pl->grid = (int)(items < wg_sms() ? items : wg_sms());
+  pl->grid = cl * (int)(items < slots ? items : slots);
   return true;
 }
 
@@ -533,12 +590,32 @@ static int wg_launch(const WgMaps& maps, WgPlan& pl, float* dw, float* db, int c
   pl.a.ws_bias = (float*)((char*)ws + pl.ws_bytes);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(wgrad_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kWgSmemBudget + 4096);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(wgrad_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)kWgSmemBudget + 4096);
     if (e != cudaSuccess) return fail((int)e, "wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_done = true;
   }
-  wgrad_umma_kernel<<<pl.grid, kWgThreads, pl.smem_bytes, st>>>(maps, pl.a);
+  if (pl.a.cta2) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(pl.grid);
+    cfg.blockDim = dim3(kWgThreads);
+    cfg.dynamicSmemBytes = pl.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, wgrad_umma_kernel<true>, maps, pl.a);
+    if (e != cudaSuccess) return fail((int)e, "wgrad: cluster launch: %s", cudaGetErrorString(e));
+  } else {
+    wgrad_umma_kernel<false><<<pl.grid, kWgThreads, pl.smem_bytes, st>>>(maps, pl.a);
+  }
   int r = check_launch("wgrad_umma");
   if (r) return r;
   dim3 grid((unsigned)((pl.a.n_total + kRedN - 1) / kRedN), (unsigned)pl.a.m_total);
