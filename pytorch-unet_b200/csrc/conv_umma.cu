@@ -317,19 +317,21 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     auto preload_bias = [&](int tile, int buf) {
       if (a.bias == nullptr) return;
       const TileCoord t = decode_tile<CL>(a, tile, rank, BN);
-      const int d = a.ndst > 1 ? min(t.n0 / a.dst_c0, a.ndst - 1) : 0;
-      const float* bp = a.bias + (t.n0 - d * a.dst_c0);
 #pragma unroll 1
       for (int wi = egrp; wi < MB * PASSES; wi += 2) {
         const int mb = wi / PASSES;
         const int c0 = (wi - mb * PASSES) * CP;
 #pragma unroll 1
         for (int col0 = c0; col0 < c0 + CP; col0 += 32) {
+          // several destinations (ConvTranspose quadrants) share one bias vector: column -> channel inside its destination
+          const int nc = t.n0 + col0;
+          const int d = a.ndst > 1 ? min(nc / a.dst_c0, a.ndst - 1) : 0;
+          const float* bp = a.bias + (nc - d * a.dst_c0);
           uint32_t bv[32];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (t.n0 + col0 + 4 * j < a.cout_total) f = *reinterpret_cast<const float4*>(bp + col0 + 4 * j);
+            if (nc + 4 * j < a.cout_total) f = *reinterpret_cast<const float4*>(bp + 4 * j);
             bv[4 * j] = __float_as_uint(f.x);
             bv[4 * j + 1] = __float_as_uint(f.y);
             bv[4 * j + 2] = __float_as_uint(f.z);
@@ -358,14 +360,15 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       const int buf = it % NBUF;
       mbar_wait(&t_full[buf], (it / NBUF) & 1);
       tc_fence_after_sync();
-      const int d = a.ndst > 1 ? min(t.n0 / a.dst_c0, a.ndst - 1) : 0;
-      const int ch0 = t.n0 - d * a.dst_c0;
-      const DView& dst = a.dst[d];
-      const bf16* mk = a.mask[d];
 #pragma unroll 1  // keep the epilogue body small: fully unrolled it was ~3000 instructions and ran out of the I-cache
       for (int wi = egrp; wi < MB * PASSES; wi += 2) {
         const int mb = wi / PASSES;
         const int col0 = (wi - mb * PASSES) * CP;
+        // destination of this 64-column pass (a tile may span several destinations, a pass never does)
+        const int d = a.ndst > 1 ? min((t.n0 + col0) / a.dst_c0, a.ndst - 1) : 0;
+        const int ch0 = t.n0 + col0 - d * a.dst_c0;
+        const DView& dst = a.dst[d];
+        const bf16* mk = a.mask[d];
         const int q = mb * 128 + quarter * 32 + lane;
         const int ty = q / a.P, tx = q - ty * a.P;
         const int oy = t.y0 + ty, ox = t.x0 + tx;
@@ -423,8 +426,8 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
           __syncwarp();
           // store side: lane (rsub, cch) moves chunk cch of rows rsub, rsub + RPI, ...
           bf16* const dp = plane ? dlo : dst.p;
-          const int col = col0 + cch * 8;
-          const bool col_ok = t.n0 + col < a.cout_total;
+          const int col = cch * 8;  // inside this pass; ch0 already carries col0
+          const bool col_ok = t.n0 + col0 + col < a.cout_total;
           long long offs[LPR];
           bf16x8 mv[LPR];
 #pragma unroll
@@ -509,7 +512,8 @@ static int pick_bn(int cout_total, int ndst, int dst_c0) {
   for (int i = 0; i < 4; ++i) {
     const int bn = cands[i];
     if (bn > g_umma_max_bn) continue;
-    if (cout_total % bn == 0 && (ndst == 1 || dst_c0 % bn == 0)) return bn;
+    // a tile may span destinations as long as no 64-column epilogue pass does
+    if (cout_total % bn == 0 && (ndst == 1 || dst_c0 % bn == 0 || (bn >= 64 && dst_c0 % 64 == 0))) return bn;
   }
   // no exact tiling: a partial last N tile is fine (weight rows past Cout are zero-filled by TMA, the epilogue predicates
   // the columns) as long as no tile straddles two destinations
@@ -521,7 +525,8 @@ static int pick_bn(int cout_total, int ndst, int dst_c0) {
 }
 
 // Chooses tile geometry (MB M-blocks of 128 positions, pitch P, TH rows) minimising issued MMA rows.
-static bool make_plan(int Ho, int Wo, int n_img, int halo, int cout_total, int ndst, int dst_c0, Plan* pl) {
+// k_work = (64-channel K chunks) x (filter taps): MMA batches per tile
+static bool make_plan(int Ho, int Wo, int n_img, int halo, int cout_total, int ndst, int dst_c0, int k_work, Plan* pl) {
   int bn = pick_bn(cout_total, ndst, dst_c0);
   if (bn == 0) return false;
   pl->halo = halo;
@@ -556,7 +561,11 @@ static bool make_plan(int Ho, int Wo, int n_img, int halo, int cout_total, int n
   if (!found) return false;
   pl->BN = bn;
   // CTA pairs (cta_group::2) split the weight tile between two pixel tiles: needs enough pixel tiles for every pair
-  pl->CL = (g_umma_cluster && bn >= 32 && (long long)((Wo + pl->TW - 1) / pl->TW) * ((Ho + pl->TH - 1) / pl->TH) * n_img >= 4) ? 2 : 1;
+  // ... and enough MMA work per tile: a pair runs in lockstep (the leader's next tile needs BOTH epilogues done), which
+  // costs more than the halved weight traffic saves when a tile is mostly epilogue (transposed conv with few input
+  // channels: measured 0.29 -> 0.33 ms at 128 -> 64 channels)
+  pl->CL = (g_umma_cluster && bn >= 32 && k_work >= 8 &&
+            (long long)((Wo + pl->TW - 1) / pl->TW) * ((Ho + pl->TH - 1) / pl->TH) * n_img >= 4) ? 2 : 1;
   pl->tiles_x = (Wo + pl->TW - 1) / pl->TW;
   pl->tiles_y = (Ho + pl->TH - 1) / pl->TH;
   pl->n_ntiles = (cout_total + bn - 1) / bn;
@@ -651,6 +660,12 @@ static int launch_plan(const TileMaps& maps, UmmaArgs& a, const Plan& pl, cudaSt
 }
 
 // ------------------------------------------------------------------ conv forward
+static int fwd_k_work(const b200_conv_fwd_params* p) {
+  int chunks = 0;
+  for (int i = 0; i < p->num_src; ++i) chunks += (p->src[i].c + 63) / 64;
+  return chunks * (p->dst.lo ? 3 : 1) * p->taps;
+}
+
 bool umma_conv_fwd_ok(const b200_conv_fwd_params* p) {
   if (!device_is_sm100()) return false;
   for (int i = 0; i < p->num_src; ++i)
@@ -658,14 +673,15 @@ bool umma_conv_fwd_ok(const b200_conv_fwd_params* p) {
   if (!aligned_view(p->dst)) return false;
   if (p->bias && reinterpret_cast<uintptr_t>(p->bias) % 16 != 0) return false;
   Plan pl;
-  return make_plan(p->dst.h, p->dst.w, p->dst.n, p->taps == 9 ? 2 : 0, p->dst.c, 1, p->dst.c, &pl);
+  return make_plan(p->dst.h, p->dst.w, p->dst.n, p->taps == 9 ? 2 : 0, p->dst.c, 1, p->dst.c, fwd_k_work(p), &pl);
 }
 
 int umma_conv_fwd(const b200_conv_fwd_params* p, cudaStream_t st) {
   if (!p->w_packed) return fail(-1, "conv_fwd (tcgen05): w_packed is required");
   const int halo = p->taps == 9 ? 2 : 0;
   Plan pl;
-  if (!make_plan(p->dst.h, p->dst.w, p->dst.n, halo, p->dst.c, 1, p->dst.c, &pl)) return fail(-1, "conv_fwd: no plan");
+  if (!make_plan(p->dst.h, p->dst.w, p->dst.n, halo, p->dst.c, 1, p->dst.c, fwd_k_work(p), &pl))
+    return fail(-1, "conv_fwd: no plan");
   TileMaps maps;
   UmmaArgs a{};
   // split tier: operand passes {hi(x) | lo(x) | hi(x)} against weights packed {hi(W) | hi(W) | lo(W)} along K
@@ -720,7 +736,7 @@ bool umma_conv_dgrad_ok(const b200_conv_dgrad_params* p) {
   }
   Plan pl;
   return make_plan(p->dst[0].h, p->dst[0].w, p->dst[0].n, p->taps == 9 ? 2 : 0, dgrad_cin(p), p->num_dst, p->dst[0].c,
-                   &pl);
+                   (p->dz.c + 63) / 64 * p->taps, &pl);
 }
 
 int umma_conv_dgrad(const b200_conv_dgrad_params* p, cudaStream_t st) {
@@ -728,7 +744,7 @@ int umma_conv_dgrad(const b200_conv_dgrad_params* p, cudaStream_t st) {
   const int halo = p->taps == 9 ? 2 : 0;
   const int cin = dgrad_cin(p);
   Plan pl;
-  if (!make_plan(p->dst[0].h, p->dst[0].w, p->dst[0].n, halo, cin, p->num_dst, p->dst[0].c, &pl))
+  if (!make_plan(p->dst[0].h, p->dst[0].w, p->dst[0].n, halo, cin, p->num_dst, p->dst[0].c, (p->dz.c + 63) / 64 * p->taps, &pl))
     return fail(-1, "conv_dgrad: no plan");
   TileMaps maps;
   UmmaArgs a{};
@@ -774,13 +790,14 @@ bool umma_convt_fwd_ok(const b200_convt_fwd_params* p) {
   if (!aligned_view(p->x) || !aligned_view(p->y)) return false;
   if (p->bias && reinterpret_cast<uintptr_t>(p->bias) % 16 != 0) return false;
   Plan pl;
-  return make_plan(p->x.h, p->x.w, p->x.n, 0, 4 * p->y.c, 4, p->y.c, &pl);
+  return make_plan(p->x.h, p->x.w, p->x.n, 0, 4 * p->y.c, 4, p->y.c, (p->x.c + 63) / 64 * (p->y.lo ? 3 : 1), &pl);
 }
 
 int umma_convt_fwd(const b200_convt_fwd_params* p, cudaStream_t st) {
   if (!p->w_packed) return fail(-1, "convt_fwd (tcgen05): w_packed is required");
   Plan pl;
-  if (!make_plan(p->x.h, p->x.w, p->x.n, 0, 4 * p->y.c, 4, p->y.c, &pl)) return fail(-1, "convt_fwd: no plan");
+  if (!make_plan(p->x.h, p->x.w, p->x.n, 0, 4 * p->y.c, 4, p->y.c, (p->x.c + 63) / 64 * (p->y.lo ? 3 : 1), &pl))
+    return fail(-1, "convt_fwd: no plan");
   TileMaps maps;
   UmmaArgs a{};
   const bool split = p->y.lo != nullptr;  // see umma_conv_fwd
@@ -819,13 +836,14 @@ bool umma_convt_dgrad_ok(const b200_convt_dgrad_params* p) {
   if (!aligned_view(p->dx) || !aligned_view(p->dy)) return false;
   if (reinterpret_cast<uintptr_t>(p->mask) % 16 != 0) return false;
   Plan pl;
-  return make_plan(p->dx.h, p->dx.w, p->dx.n, 0, p->dx.c, 1, p->dx.c, &pl);
+  return make_plan(p->dx.h, p->dx.w, p->dx.n, 0, p->dx.c, 1, p->dx.c, 4 * ((p->dy.c + 63) / 64), &pl);
 }
 
 int umma_convt_dgrad(const b200_convt_dgrad_params* p, cudaStream_t st) {
   if (!p->w_packed) return fail(-1, "convt_dgrad (tcgen05): w_packed is required");
   Plan pl;
-  if (!make_plan(p->dx.h, p->dx.w, p->dx.n, 0, p->dx.c, 1, p->dx.c, &pl)) return fail(-1, "convt_dgrad: no plan");
+  if (!make_plan(p->dx.h, p->dx.w, p->dx.n, 0, p->dx.c, 1, p->dx.c, 4 * ((p->dy.c + 63) / 64), &pl))
+    return fail(-1, "convt_dgrad: no plan");
   TileMaps maps;
   UmmaArgs a{};
   a.num_a = 4;

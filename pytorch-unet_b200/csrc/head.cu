@@ -31,7 +31,7 @@ struct HeadArgs {
 };
 
 template <int KMAX, int VEC, int MODE>
-__global__ void __launch_bounds__(kHeadThreads, KMAX == 2 ? 4 : 1) head_kernel(HeadArgs a) {
+__global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadArgs a) {
   extern __shared__ float smem[];
   const int c = a.x.c, K = a.k;
   float* sw = smem;           // [K][c]
@@ -67,47 +67,31 @@ __global__ void __launch_bounds__(kHeadThreads, KMAX == 2 ? 4 : 1) head_kernel(H
   const unsigned upr = (unsigned)(a.x.w + slots - 1) / slots;       // units per row
   const unsigned units = (unsigned)a.x.n * a.x.h * upr;
   (void)npix;
-  // 64-channel fast path (the U-Net's head input): one vector per lane, and the NEXT unit's vector is requested before
-  // this unit is processed — with a single dependent 16-byte load per thread and iteration the kernel was bound by
-  // memory latency at ~2 TB/s.
-  const bool fast = VEC == 8 && nvec == 8 && a.x.lo == nullptr;
-  auto unit_ptr = [&](unsigned u, int& n, int& ih, int& iw) -> const bf16* {
-    const unsigned row = u / upr, cb = u - row * upr;
-    n = (int)(row / a.x.h);
-    ih = (int)(row - (unsigned)n * a.x.h);
-    iw = (int)(cb * slots) + slot;
-    return a.x.p + a.x.off(n, ih, min(iw, a.x.w - 1));
-  };
-  bf16x8 nxt = make_uint4(0, 0, 0, 0);
-  if (fast && blockIdx.x < units) {
-    int n, ih, iw;
-    const bf16* q = unit_ptr(blockIdx.x, n, ih, iw);
-    nxt = *reinterpret_cast<const bf16x8*>(q + lane8 * 8);
-  }
   for (unsigned u = blockIdx.x; u < units; u += gridDim.x) {
-    int n, ih, iw;
-    const bf16* xp = unit_ptr(u, n, ih, iw);
-    const unsigned row = u / upr;
+    const unsigned row = u / upr, cb = u - row * upr;
+    const int n = (int)(row / a.x.h), ih = (int)(row - (unsigned)n * a.x.h);
+    const int iw = (int)(cb * slots) + slot;
     const bool live = iw < a.x.w;
     const long long p = (long long)row * a.x.w + iw;
-    const bf16x8 cur = nxt;
-    if (fast && u + gridDim.x < units) {
-      int n2, ih2, iw2;
-      const bf16* q = unit_ptr(u + gridDim.x, n2, ih2, iw2);
-      nxt = *reinterpret_cast<const bf16x8*>(q + lane8 * 8);
-    }
+    const bf16* xp = a.x.p + a.x.off(n, ih, iw);
     float z[KMAX];
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) z[k] = 0.f;
     float xmine[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) xmine[j] = 0.f;
+    // backward: request the ReLU mask of this lane's dx vector together with x, not after the softmax that depends on x
+    // (two dependent memory round trips per iteration otherwise).  Without BatchNorm the mask IS x: nothing to load.
+    const bool mask_is_x = a.mask == a.x.p && a.dx.sn == a.x.sn && a.dx.sh == a.x.sh && a.dx.sw == a.x.sw;
+    bf16x8 mvec = make_uint4(0, 0, 0, 0);
+    if ((MODE == HEAD_BWD || MODE == HEAD_CE_BWD) && VEC == 8 && a.mask && !mask_is_x && live && myv < nvec && a.dx.p)
+      mvec = *reinterpret_cast<const bf16x8*>(a.mask + a.dx.off(n, ih, iw) + myv * VEC);
     if (live) {
       for (int v = lane8; v < nvec; v += 8) {
         float xv[VEC];
         if (VEC == 8) {
           float t[8];
-          unpack8(fast ? cur : *reinterpret_cast<const bf16x8*>(xp + v * 8), t);
+          unpack8(*reinterpret_cast<const bf16x8*>(xp + v * 8), t);
 #pragma unroll
           for (int j = 0; j < VEC; ++j) xv[j] = t[j];
           if (a.x.lo) {  // split tier (forward modes): x = hi + lo
@@ -208,9 +192,9 @@ __global__ void __launch_bounds__(kHeadThreads, KMAX == 2 ? 4 : 1) head_kernel(H
         if (a.mask) {
           if (VEC == 8) {
             float t[8];
-            unpack8(*reinterpret_cast<const bf16x8*>(a.mask + o), t);
+            unpack8(mvec, t);
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) r[j] = t[j] > 0.f ? r[j] : 0.f;
+            for (int j = 0; j < VEC; ++j) r[j] = (mask_is_x ? xmine[j] : t[j]) > 0.f ? r[j] : 0.f;
           } else {
             r[0] = bf2f(a.mask[o]) > 0.f ? r[0] : 0.f;
           }

@@ -58,39 +58,15 @@ __device__ __forceinline__ void store_fwd(bf16* out, long long row_off, int k, i
   }
 }
 
-__global__ void __launch_bounds__(kAdamThreads)
-adam_pack_kernel(const b200_adam_job* __restrict__ jobs, int num_jobs, AdamHyper hyper, const float* __restrict__ step) {
-  __shared__ float tile[kTileA][kTileB * 9 + 1];
-  // job of this block: last j with block0 <= blockIdx.x
-  int lo = 0, hi = num_jobs - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (jobs[mid].block0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
-  }
-  const b200_adam_job J = jobs[lo];
-  const int blk = (int)blockIdx.x - J.block0;
-  const AdamCoef c = load_coef(hyper, step);
-
-  if (J.kind == 0) {
-    const long long base = (long long)blk * kAdamPlainPerBlock;
-#pragma unroll
-    for (int u = 0; u < kAdamPlainPerBlock / kAdamThreads; ++u) {
-      const long long i = base + u * kAdamThreads + threadIdx.x;
-      if (i < J.numel) {
-        float m = J.exp_avg[i], v = J.exp_avg_sq[i];
-        J.param[i] = adam_update(c, J.param[i], J.grad[i], m, v);
-        J.exp_avg[i] = m;
-        J.exp_avg_sq[i] = v;
-      }
-    }
-    return;
-  }
-
-  // weight tile [a0, a0 + 16) x [b0, b0 + 32) x taps of w[dim0][dim1][taps]
-  const int A = J.dim0, B = J.dim1, T = J.taps;
+// One [16 x 32 x T] weight tile: update, then the two packed layouts.  T (filter taps) and FULL (a complete tile) are
+// compile-time so that the index arithmetic is shifts and multiplies, not divisions by runtime values.
+template <int T, bool FULL>
+__device__ __forceinline__ void adam_tile(const b200_adam_job& J, const AdamCoef& c, int blk,
+                                          float (*tile)[kTileB * 9 + 1]) {
+  const int A = J.dim0, B = J.dim1;
   const int tiles_b = (B + kTileB - 1) / kTileB;
   const int a0 = (blk / tiles_b) * kTileA, b0 = (blk % tiles_b) * kTileB;
-  const int nb = min(kTileB, B - b0), na = min(kTileA, A - a0);
+  const int nb = FULL ? kTileB : min(kTileB, B - b0), na = FULL ? kTileA : min(kTileA, A - a0);
   const int run = nb * T;  // contiguous floats per a-row
   for (int idx = threadIdx.x; idx < na * run; idx += kAdamThreads) {
     const int al = idx / run, r = idx - al * run;
@@ -146,6 +122,53 @@ adam_pack_kernel(const b200_adam_job* __restrict__ jobs, int num_jobs, AdamHyper
   }
 }
 
+template <int T>
+__device__ __forceinline__ void adam_tile_t(const b200_adam_job& J, const AdamCoef& c, int blk,
+                                            float (*tile)[kTileB * 9 + 1]) {
+  const int tiles_b = (J.dim1 + kTileB - 1) / kTileB;
+  const int a0 = (blk / tiles_b) * kTileA, b0 = (blk % tiles_b) * kTileB;
+  if (a0 + kTileA <= J.dim0 && b0 + kTileB <= J.dim1) adam_tile<T, true>(J, c, blk, tile);
+  else adam_tile<T, false>(J, c, blk, tile);
+}
+
+__global__ void __launch_bounds__(kAdamThreads)
+adam_pack_kernel(const b200_adam_job* __restrict__ jobs, int num_jobs, AdamHyper hyper, const float* __restrict__ step) {
+  __shared__ float tile[kTileA][kTileB * 9 + 1];
+  __shared__ AdamCoef s_coef;
+  if (threadIdx.x == 0) s_coef = load_coef(hyper, step);  // two double-precision pow(): once per block, not per thread
+  // job of this block: last j with block0 <= blockIdx.x
+  int lo = 0, hi = num_jobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].block0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const b200_adam_job J = jobs[lo];
+  const int blk = (int)blockIdx.x - J.block0;
+  __syncthreads();
+  const AdamCoef c = s_coef;
+
+  if (J.kind == 0) {
+    const long long base = (long long)blk * kAdamPlainPerBlock;
+#pragma unroll
+    for (int u = 0; u < kAdamPlainPerBlock / kAdamThreads; ++u) {
+      const long long i = base + u * kAdamThreads + threadIdx.x;
+      if (i < J.numel) {
+        float m = J.exp_avg[i], v = J.exp_avg_sq[i];
+        J.param[i] = adam_update(c, J.param[i], J.grad[i], m, v);
+        J.exp_avg[i] = m;
+        J.exp_avg_sq[i] = v;
+      }
+    }
+    return;
+  }
+  switch (J.taps) {
+    case 9: adam_tile_t<9>(J, c, blk, tile); break;
+    case 4: adam_tile_t<4>(J, c, blk, tile); break;
+    case 1: adam_tile_t<1>(J, c, blk, tile); break;
+    default: break;  // adam_plan only admits taps 1, 4, 9 for weight jobs
+  }
+}
+
 // The job table travels to the device as kernel ARGUMENTS (32 jobs per launch): no pinned staging buffer, no copy to
 // order against, and a CUDA graph captures the values themselves.
 struct JobChunk {
@@ -171,7 +194,7 @@ int b200unet_adam_plan(b200_adam_job* jobs, int num_jobs) {
     if (J.kind == 0) {
       nb = (J.numel + kAdamPlainPerBlock - 1) / kAdamPlainPerBlock;
     } else {
-      B200_REQUIRE(J.dim0 > 0 && J.dim1 > 0 && J.taps >= 1 && J.taps <= 9 &&
+      B200_REQUIRE(J.dim0 > 0 && J.dim1 > 0 && (J.taps == 1 || J.taps == 4 || J.taps == 9) &&
                        (long long)J.dim0 * J.dim1 * J.taps == J.numel,
                    "adam_plan: job %d: extents do not match numel", j);
       B200_REQUIRE(J.kind != 1 || (J.src0_c > 0 && J.src0_c <= J.dim1), "adam_plan: job %d: bad src0_c", j);
