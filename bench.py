@@ -145,7 +145,7 @@ def run_reference(args):
             "config": {"workload": WORKLOAD, "sample": "batch 1 per step (CPU)"},
             "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ our arm (B200)
@@ -395,7 +395,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": xh.numel() * 4 + yh.numel() * 8, "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "conv_breakdown": breakdown}
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if args.detail:
         with open(args.detail, "w") as fh:
             fh.write(timer.detail_table() + "\n")
@@ -403,7 +403,30 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line on the first
+    communicator), so everything else that goes to fd 1 is re-routed to stderr and the JSON line is written to the
+    original stdout at the end."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

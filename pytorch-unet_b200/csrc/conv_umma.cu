@@ -310,6 +310,17 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     uint4* stg = reinterpret_cast<uint4*>(sOut + (warp - 3) * 4096);   // [32 rows][LPR chunks] of 16 B
     const int rsub = lane / LPR, cch = lane % LPR;
     const uint32_t lane_base = uint32_t(quarter * 32) << 16;
+    // position of this lane's accumulator row inside the tile, per M-block: fixed for the whole kernel (P is), so the
+    // division is paid once here and not in every (tile, M-block, pass) iteration
+    int pos_ty[MB], pos_tx[MB];
+#pragma unroll
+    for (int mb = 0; mb < MB; ++mb) {
+      const int q = mb * 128 + quarter * 32 + lane;
+      pos_ty[mb] = q / a.P;
+      pos_tx[mb] = q - pos_ty[mb] * a.P;
+      if (pos_ty[mb] >= a.TH || pos_tx[mb] >= a.TW) pos_ty[mb] = 1 << 20;  // halo column / beyond the tile: never stored
+    }
+    const uint32_t stg_s = smem_u32(stg);  // explicit shared-memory accesses (generic LD/ST cost an address-space check)
 
     // writes bias[n0 .. n0+BN) into the rows of accumulator buffer `buf` — each warp exactly the (M-block, column
     // pass) regions it drains itself, so a fast warp never overwrites a region its partner is still reading
@@ -369,11 +380,17 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
         const int ch0 = t.n0 + col0 - d * a.dst_c0;
         const DView& dst = a.dst[d];
         const bf16* mk = a.mask[d];
-        const int q = mb * 128 + quarter * 32 + lane;
-        const int ty = q / a.P, tx = q - ty * a.P;
+        int ty = pos_ty[0], tx = pos_tx[0];
+#pragma unroll
+        for (int m = 1; m < MB; ++m)
+          if (m == mb) {
+            ty = pos_ty[m];
+            tx = pos_tx[m];
+          }
         const int oy = t.y0 + ty, ox = t.x0 + tx;
-        const bool valid = ty < a.TH && tx < a.TW && oy < a.Ho && ox < a.Wo;
-        const long long off = valid ? dst.off(t.n, oy, ox) + ch0 : -1;  // -1 = nothing to store for this position
+        const bool valid = oy < a.Ho && ox < a.Wo;
+        // element offset from the destination's base pointer; fits 32 bits (checked on the host); -1 = nothing to store
+        const int off = valid ? (int)(dst.off(t.n, oy, ox) + ch0) : -1;
         const uint32_t taddr = tmem_base + buf * (MB * BN) + mb * BN + lane_base;
         bf16* const dlo = a.dst_lo[d];
         // split tier: a second pass over the same accumulators writes the low-order plane (the TMEM read is repeated
@@ -407,7 +424,7 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
                 c.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
                 c.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
               }
-              stg[lane * LPR + (j ^ (lane & (LPR - 1)))] = c;
+              st_shared_v4(stg_s + (uint32_t)(lane * LPR + (j ^ (lane & (LPR - 1)))) * 16, c);
             }
           } else {
             // lo = bf16(v' - bf16(v')), v' = the (ReLU'd) fp32 result
@@ -420,36 +437,42 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
                 if (a.relu) x = fmaxf(x, 0.f);
                 r[e] = split_lo(x, bf2f(f2bf(x)));
               }
-              stg[lane * LPR + (j ^ (lane & (LPR - 1)))] = pack8(r);
+              st_shared_v4(stg_s + (uint32_t)(lane * LPR + (j ^ (lane & (LPR - 1)))) * 16, pack8(r));
             }
           }
           __syncwarp();
           // store side: lane (rsub, cch) moves chunk cch of rows rsub, rsub + RPI, ...
-          bf16* const dp = plane ? dlo : dst.p;
-          const int col = cch * 8;  // inside this pass; ch0 already carries col0
-          const bool col_ok = t.n0 + col0 + col < a.cout_total;
-          long long offs[LPR];
-          bf16x8 mv[LPR];
+          bf16* const dp = (plane ? dlo : dst.p) + cch * 8;
+          const bool col_ok = t.n0 + col0 + cch * 8 < a.cout_total;
+          int offs[LPR];
 #pragma unroll
-          for (int i = 0; i < LPR; ++i) {
-            offs[i] = __shfl_sync(0xffffffffu, off, i * RPI + rsub);
-            if (!col_ok) offs[i] = -1;
-            if (mk && offs[i] >= 0) mv[i] = *reinterpret_cast<const bf16x8*>(mk + offs[i] + col);
-          }
+          for (int i = 0; i < LPR; ++i) offs[i] = __shfl_sync(0xffffffffu, off, i * RPI + rsub);
+          if (col_ok) {
+            if (mk) {  // dgrad: zero where the producer's ReLU was inactive (mask <= 0)
+              bf16x8 mv[LPR];
 #pragma unroll
-          for (int i = 0; i < LPR; ++i) {
-            const int R = i * RPI + rsub;
-            if (offs[i] >= 0) {
-              uint4 c = stg[R * LPR + (cch ^ (R & (LPR - 1)))];
-              if (mk) {  // dgrad: zero where the producer's ReLU was inactive (mask <= 0)
-                float f[8], m[8];
-                unpack8(c, f);
-                unpack8(mv[i], m);
+              for (int i = 0; i < LPR; ++i)
+                if (offs[i] >= 0) mv[i] = *reinterpret_cast<const bf16x8*>(mk + cch * 8 + offs[i]);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = m[j] > 0.f ? f[j] : 0.f;
-                c = pack8(f);
+              for (int i = 0; i < LPR; ++i) {
+                const int R = i * RPI + rsub;
+                if (offs[i] >= 0) {
+                  const uint4 c = ld_shared_v4(stg_s + (uint32_t)(R * LPR + (cch ^ (R & (LPR - 1)))) * 16);
+                  float f[8], m[8];
+                  unpack8(c, f);
+                  unpack8(mv[i], m);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) f[j] = m[j] > 0.f ? f[j] : 0.f;
+                  *reinterpret_cast<uint4*>(dp + offs[i]) = pack8(f);
+                }
               }
-              *reinterpret_cast<uint4*>(dp + offs[i] + col) = c;
+            } else {
+#pragma unroll
+              for (int i = 0; i < LPR; ++i) {
+                const int R = i * RPI + rsub;
+                if (offs[i] >= 0)
+                  *reinterpret_cast<uint4*>(dp + offs[i]) = ld_shared_v4(stg_s + (uint32_t)(R * LPR + (cch ^ (R & (LPR - 1)))) * 16);
+              }
             }
           }
           __syncwarp();
@@ -490,8 +513,10 @@ struct Plan {
 };
 
 static bool aligned_view(const b200_view& v) {
+  // the epilogue addresses a destination with 32-bit element offsets from its base pointer
+  const int64_t span = (int64_t)(v.n - 1) * v.stride_n + (int64_t)(v.h - 1) * v.stride_h + (int64_t)(v.w - 1) * v.stride_w + v.c;
   return v.c % 8 == 0 && reinterpret_cast<uintptr_t>(v.ptr) % 16 == 0 && reinterpret_cast<uintptr_t>(v.lo) % 16 == 0 &&
-         v.stride_w % 8 == 0 && v.stride_h % 8 == 0 && (v.n == 1 || v.stride_n % 8 == 0);
+         v.stride_w % 8 == 0 && v.stride_h % 8 == 0 && (v.n == 1 || v.stride_n % 8 == 0) && span < (int64_t(1) << 31);
 }
 
 static b200_view lo_plane(const b200_view& v) {  // the low-order plane of a split-tier view, as a plain view
