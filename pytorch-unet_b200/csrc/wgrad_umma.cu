@@ -441,6 +441,10 @@ wgrad_umma_reduce_kernel(const float* __restrict__ ws, int splits, int taps, int
 static int g_wgrad_n128 = getenv("B200UNET_WGRAD_N64") ? 0 : 1;
 static int g_wgrad_min_stages = getenv("B200UNET_WGRAD_MIN_STAGES") ? atoi(getenv("B200UNET_WGRAD_MIN_STAGES")) : 2;
 static int g_wgrad_cta2 = getenv("B200UNET_WGRAD_NO_PAIRS") ? 0 : 1;
+// cost-model cycles per TMA instruction of a stage (the row operand arrives one tile row per instruction): measured on
+// the whole training step 0 -> 31.1 ms, 30 -> 30.7, 70 -> 30.2, 100/150 -> +0.3; without it the planner picked 13 x 19
+// pixel tiles for the first layer (19 tiny row loads per stage) and 0.46 ms where 114 x 2 tiles take 0.38
+static double g_wgrad_tma_cost = getenv("B200UNET_WGRAD_TMA_COST") ? atof(getenv("B200UNET_WGRAD_TMA_COST")) : 70.0;
 
 struct WgPlan {
   WgArgs a;
@@ -524,7 +528,8 @@ static bool wg_make_plan(int mode, int Ho, int Wo, int n_img, int m_total, int n
       // bytes moved L2 -> SMEM at ~32 B/cycle/SM; whichever is larger, plus a fixed per-tile cost
       const double t_mma = mma_groups * (kt / 16) * mma_cycles;
       const double t_load = ((double)r_loads * TH * TW * 128 + (double)g_tiles * (TH + a.halo) * P * 128) / 32.0;
-      const double cost = (double)tiles * passes * ((t_mma > t_load ? t_mma : t_load) + 300.0);
+      const double t_ops = g_wgrad_tma_cost * ((double)r_loads * TH + g_tiles);  // per-TMA-instruction cost (row loads)
+      const double cost = (double)tiles * passes * ((t_mma > t_load ? t_mma : t_load) + 300.0 + t_ops);
       if (cost < best) {
         best = cost;
         found = true;
@@ -572,6 +577,12 @@ static bool wg_make_plan(int mode, int Ho, int Wo, int n_img, int m_total, int n
   pl->smem_bytes = (uint32_t)a.stages * a.stage_bytes + kWgOnesBytes + 1024 + 256;
   const long long items = base_items * splits;
   pl->grid = cl * (int)(items < slots ? items : slots);
+  static const bool dbg = getenv("B200UNET_DEBUG_PLAN") != nullptr;
+  if (dbg)
+    fprintf(stderr, "[wgrad plan] mode %d %dx%dx%d m %d n %d taps %d: paired %d cta2 %d nbw %d groups %d kt %d P %d TH %d TW %d "
+            "stages %d stage_bytes %u splits %d items %lld grid %d tiles %lld\n", mode, n_img, Ho, Wo, m_total, n_total, taps,
+            a.paired, a.cta2, a.nbw, a.tap_groups, a.kt_rows, a.P, a.TH, a.TW, a.stages, a.stage_bytes, a.splits, items,
+            pl->grid, tiles);
   return true;
 }
 
