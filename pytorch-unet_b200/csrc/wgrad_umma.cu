@@ -14,8 +14,12 @@
 // Accumulators: one [128 x 64] fp32 block per tap in TMEM.  9 taps x 64 columns do not fit in 512, so
 //   * Cout >= 128: a 3x3 runs as two tap groups (5 + 4) executed back to back by the same CTA;
 //   * Cout <= 64 ("paired" mode): the second 64-lane half of the M = 128 MMA would be idle, so it is given the SAME dz
-//     tile stored one pixel row later.  One MMA with gathered shift sigma then yields tap sigma+1 on lanes 0..63 and
-//     tap sigma on lanes 64..127: the nine taps need 6 MMAs (sigma = rP and rP+2) and 384 columns — one pass.
+//     tile stored one pixel (one 128-byte shared-memory row) later: lanes 0..63 see filter column s+1, lanes 64..127
+//     column s.  The N side is widened the same way: N = 192 = the x tile read at IMAGE-row shifts 0, 1, 2 — three
+//     64-channel groups whose descriptor stride (LBO) is one tile pitch, P*128 bytes, i.e. three overlapping views of
+//     the same buffer.  One MMA (full tensor rate) yields the 6 taps of filter columns 0 and 1, a second one at a
+//     gathered shift of 2 pixels the column 2: 2 MMAs / 192 cycles per K step instead of 6 N = 64 MMAs / 288 cycles,
+//     384 TMEM columns, one pass.
 // Bias gradient: one extra N = 16 MMA per K step against a block of ones (column sums of dz on the tensor core).
 // CTA pairs (cta2 mode, tcgen05 cta_group::2; >= 256 row channels and N = 128): two CTAs take the two 128-channel M
 // blocks of the same (split, N block) and execute ONE MMA of M = 256 per tap and K step; each loads its own R tile and
@@ -89,7 +93,7 @@ __device__ __forceinline__ WgItem decode_item(const WgArgs& a, int item, int ran
   w.grp = grp;
   if (a.paired) {
     w.tap0 = 0;
-    w.ntap = 6;
+    w.ntap = 2;  // MMAs per K step (gathered shifts 0 and 2P)
   } else {
     const int per = (a.taps + a.tap_groups - 1) / a.tap_groups;
     w.tap0 = w.grp * per;
@@ -209,16 +213,18 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
   } else if (warp == 1) {
     // The whole warp runs the control flow so that every address / descriptor is warp-uniform (lives in uniform
     // registers, no per-MMA R2UR/ELECT sequences); one elected lane issues the tcgen05 instructions.
-    const uint32_t idesc = umma_idesc_bf16(128 * cl, a.nbw, 1, 1);  // both operands MN-major
+    const int mma_n = a.paired ? 192 : a.nbw;                        // paired: three row-shifted views of the x tile
+    const uint32_t idesc = umma_idesc_bf16(128 * cl, mma_n, 1, 1);   // both operands MN-major
     const uint32_t idesc_bias = umma_idesc_bf16(128 * cl, 16, 1, 1);
     const uint64_t hi_r = umma_desc_hi_sw128(a.r_blk_bytes, 1024);
-    const uint64_t hi_g = umma_desc_hi_sw128(a.g_tile_bytes, 1024);  // LBO = distance of the second 64-channel sub-tile
+    // LBO = distance of the next 64-channel group: the second sub-tile, or (paired) the same tile one image row later
+    const uint64_t hi_g = umma_desc_hi_sw128(a.paired ? (uint32_t)a.P * 128u : a.g_tile_bytes, 1024);
     const uint64_t ones_desc = umma_desc(umma_desc_hi_sw128(a.r_blk_bytes, 1024), smem_u32(ones));
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
     const int ksteps = a.kt_rows / 16;
-    const int nbw = a.nbw;
+    const int nbw = mma_n;
     const uint32_t stage_bytes = a.stage_bytes, r_blk_bytes = a.r_blk_bytes;
     const int n_stages = a.stages;
     // cta2: the leader issues for the pair; the peer's warp only took part in the TMEM allocation
@@ -233,7 +239,7 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
           uint32_t o = 0;
           if (j < w.ntap) {
             if (a.paired) {
-              o = (uint32_t)((j >> 1) * a.P + (j & 1) * 2) * 8;  // sigma = r*P + {0, 2}; 128 B = 8 units
+              o = (uint32_t)(2 * j) * 8;  // gathered shift of 0 / 2 pixels; 128 B = 8 descriptor units
             } else if (a.mode == 0) {
               const int tap = w.tap0 + j;
               const int r = tap / a.kx, sx = tap - r * a.kx;
@@ -317,28 +323,29 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
         tc_fence_after_sync();
         const int row = quarter * 32 + lane;           // TMEM lane = accumulator row
         const bool empty_item = w.tile1 <= w.tile0;    // no MMA was issued: the accumulator holds stale data
-        for (int j = 0; j < w.ntap; ++j) {
-          int tap, m;
+        const int nacc = a.paired ? 6 : w.ntap;  // [128 x 64|128] accumulator blocks to drain
+        for (int j = 0; j < nacc; ++j) {
+          int tap, m, tcol;
           bool live = true;
           if (a.paired) {
-            const int r = j >> 1;
-            if (row < 64) {  // tap sigma + 1: only sigma = rP gives a real tap (r, 1)
-              tap = r * 3 + 1;
-              m = row;
-              live = (j & 1) == 0;
-            } else {         // tap sigma: (r, 0) or (r, 2)
-              tap = r * 3 + (j & 1) * 2;
-              m = row - 64;
-            }
+            // MMA jm (gathered shift of 2*jm pixels), column group g = filter row g; lanes 0..63 hold filter column
+            // 2*jm + 1 (the dz copy stored one pixel later), lanes 64..127 filter column 2*jm
+            const int jm = j / 3, g = j - jm * 3;
+            const int fc = 2 * jm + (row < 64 ? 1 : 0);
+            live = fc <= 2;
+            tap = g * 3 + fc;
+            m = row & 63;
+            tcol = jm * 192 + g * 64;
           } else {
             tap = w.tap0 + j;
             m = w.mb * 128 + row;
+            tcol = j * a.nbw;
           }
           float* out = a.ws + (((long long)w.split * a.taps + tap) * a.m_pad + m) * a.n_pad + w.nb * a.nbw;
 #pragma unroll 1
           for (int col0 = 0; col0 < a.nbw; col0 += 32) {
             uint32_t v[32];
-            tmem_ld_32x32(tmem_base + j * a.nbw + col0 + (uint32_t(quarter * 32) << 16), v);
+            tmem_ld_32x32(tmem_base + tcol + col0 + (uint32_t(quarter * 32) << 16), v);
             tmem_ld_wait();
             if (live) {
 #pragma unroll
@@ -506,8 +513,8 @@ static bool wg_make_plan(int mode, int Ho, int Wo, int n_img, int m_total, int n
   const int cl = a.cta2 ? 2 : 1;
   const int g_tiles = (mode == 1 ? taps : 1) * (a.nbw / 64) / cl;  // gathered sub-tiles per CTA and stage
   const int r_loads = a.paired ? 2 : a.r_blocks;
-  const double mma_groups = a.paired ? 6.0 : (taps == 9 ? (a.nbw == 128 ? 3.0 : 4.5) : (double)taps);
-  const double mma_cycles = a.nbw == 128 ? 64.0 : 48.0;
+  const double mma_groups = a.paired ? 2.0 : (taps == 9 ? (a.nbw == 128 ? 3.0 : 4.5) : (double)taps);
+  const double mma_cycles = a.paired ? 96.0 : (a.nbw == 128 ? 64.0 : 48.0);
   const double passes = a.tap_groups;
   // tile geometry: kt_rows (multiple of 16) K rows per tile
   double best = 1e30;

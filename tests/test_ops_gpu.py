@@ -182,6 +182,9 @@ CONV_CASES = [
     (1, (256,), 128, 6, 6, 1, 0),
     (3, (64,), 64, 40, 70, 3, 0),
     (1, (512,), 512, 10, 12, 3, 0),
+    # enough pixel tiles and channels for CTA pairs (cta_group::2) in all three passes
+    (2, (256,), 256, 30, 34, 3, 1),
+    (1, (128, 128), 256, 26, 30, 3, 0),
     # first-layer kernels (1..4 input channels, cout % 16 == 0)
     (2, (3,), 32, 19, 23, 3, 1),
     (1, (2,), 16, 9, 30, 3, 0),
@@ -234,7 +237,8 @@ def test_conv_fwd_dgrad_wgrad(ops, case, impl_name):
         o += c
 
 
-CONVT_CASES = [(2, 64, 32, 7, 9), (1, 8, 4, 5, 5), (1, 128, 64, 12, 10), (1, 1024, 512, 4, 4), (2, 16, 16, 3, 6)]
+CONVT_CASES = [(2, 64, 32, 7, 9), (1, 8, 4, 5, 5), (1, 128, 64, 12, 10), (1, 1024, 512, 4, 4), (2, 16, 16, 3, 6),
+               (2, 256, 128, 24, 28), (1, 512, 256, 20, 22)]  # the last two: CTA pairs
 
 
 @pytest.mark.parametrize("case", CONVT_CASES, ids=[str(c) for c in CONVT_CASES])
