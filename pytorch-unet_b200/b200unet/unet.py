@@ -178,6 +178,7 @@ class UNet(nn.Module):
         self._grad_ready: Optional[Callable[[str], None]] = None
         self._grads_done: Optional[Callable[[], None]] = None
         self._pack_cache: Dict[Tuple[str, int], dict] = {}
+        self._train_forwards = 0  # training-mode forwards so far: eval-mode packs are reused only within one value
 
     # ---------------------------------------------------------------- public API
     def invalidate_packs(self) -> None:
@@ -294,16 +295,19 @@ class UNet(nn.Module):
     def _packed(self, name: str, w: torch.Tensor, mode: int, src_c=None, transposed_conv: bool = False) -> torch.Tensor:
         """Packed bf16 operand copy of weight `name` (mode: 0 forward, 1 backward-data, 2 forward of the split tier).
         The buffer of a (name, mode) entry is persistent — a repack writes into it — so that `FusedAdam` can rewrite
-        it inside its own kernel.  An entry is REUSED without repacking only if FusedAdam stamped it after its last
-        update and the parameter still has that storage and autograd version; with any other optimizer every call
-        repacks (torch's own fused Adam, for one, updates parameters without bumping their version, so a cache keyed
-        on versions alone would serve stale weights).  Internally padded parameters are fresh copies per call."""
+        it inside its own kernel.  An entry is REUSED without repacking only if the parameter still has that storage
+        and autograd version AND either FusedAdam stamped it after its last update, or the module is in eval mode and
+        the entry was packed in eval mode with no training-mode forward since (inference: weights are static).  In
+        training with any other optimizer every call repacks — torch's own fused Adam, for one, updates parameters
+        without bumping their version, so a cache keyed on versions alone would serve stale weights.  Internally padded
+        parameters are fresh copies per call."""
         if name in self._padspec:
             return (ops.pack_convt_weight(w.detach(), mode) if transposed_conv
                     else ops.pack_conv_weight(w.detach(), src_c if src_c is not None else [w.shape[1]], mode))
         key = (name, mode)
         e = self._pack_cache.get(key)
-        if e is not None and e["stamped"] and e["version"] == w._version and e["ptr"] == w.data_ptr():
+        if e is not None and e["version"] == w._version and e["ptr"] == w.data_ptr() and (
+                e["stamped"] or (not self.training and e["eval_epoch"] == self._train_forwards)):
             return e["tensor"]
         out = e["tensor"] if e is not None and e["tensor"].device == w.device else None
         if transposed_conv:
@@ -312,7 +316,8 @@ class UNet(nn.Module):
             src_c = list(src_c) if src_c is not None else [w.shape[1]]
             packed = ops.pack_conv_weight(w.detach(), src_c, mode, out=out)
         self._pack_cache[key] = {"version": w._version, "ptr": w.data_ptr(), "tensor": packed, "mode": mode,
-                                 "src_c": src_c, "transposed": transposed_conv, "stamped": False}
+                                 "src_c": src_c, "transposed": transposed_conv, "stamped": False,
+                                 "eval_epoch": self._train_forwards if not self.training else -1}
         return packed
 
     def _new_grad(self, name: str, like: torch.Tensor) -> torch.Tensor:
@@ -389,6 +394,8 @@ class UNet(nn.Module):
         return cur[0], rec["a1"]
 
     def _run_forward(self, x, labels, P, tape):
+        if self.training:
+            self._train_forwards += 1
         P = self._padded_params(P)
         if tape is not None:
             tape.P = P

@@ -203,6 +203,45 @@ def test_eval_mode_and_no_grad_match_oracle():
     assert torch.equal(model.state_dict()["down_path.0.block.2.running_mean"].cpu(), sd["down_path.0.block.2.running_mean"])
 
 
+def test_eval_forward_reuses_packed_weights_and_sees_updates():
+    """Inference: the bf16 operand copies are packed once and reused while the weights are unchanged; any in-place
+    update (version bump) or an intervening training step makes the next forward repack."""
+    import b200unet
+    spec = O.UNetSpec(1, 2, 3, 6, False, False, "upconv")
+    sd = O.init_params(spec, seed=2)
+    model = build(spec.__dict__).cuda()
+    model.load_state_dict(sd)
+    model.eval()
+    lib = b200unet.load_library()
+    x = torch.randn(1, 1, 60, 60, device="cuda")
+    with torch.no_grad():
+        n0 = lib.b200unet_launch_count()
+        o1 = model(x)
+        n1 = lib.b200unet_launch_count()
+        o2 = model(x)
+        n2 = lib.b200unet_launch_count()
+        assert torch.equal(o1, o2)
+        assert (n2 - n1) < (n1 - n0)          # no pack launches the second time
+        model.down_path[0].block[2].weight.mul_(0.5)   # in-place update -> version bump -> repack
+        o3 = model(x)
+        sd2 = {k: v.clone() for k, v in model.state_dict().items()}
+        ref = O.forward({k: v.cpu() for k, v in sd2.items()}, x.cpu(), spec, training=False)
+        assert rel_l2(o3.cpu(), ref) < TOL_LOGITS
+        assert rel_l2(o3, o1) > 1e-2
+    # a training step with torch's fused Adam (which does not bump versions) must not leave stale copies behind
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2, fused=True)
+    y = torch.randint(0, 2, (1, 20, 20), device="cuda")
+    loss = model.loss(x, y)
+    loss.backward()
+    opt.step()
+    model.eval()
+    with torch.no_grad():
+        o4 = model(x)
+    ref4 = O.forward({k: v.detach().cpu() for k, v in model.state_dict().items()}, x.cpu(), spec, training=False)
+    assert rel_l2(o4.cpu(), ref4) < TOL_LOGITS
+
+
 def test_two_forwards_then_backward():
     """The repo's own trainer runs the U-Net on both images of a pair before backward (network_modules.py:123-132)."""
     spec = O.UNetSpec(1, 2, 2, 3, False, False, "upconv")
