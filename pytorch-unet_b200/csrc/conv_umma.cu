@@ -389,8 +389,9 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
           }
         const int oy = t.y0 + ty, ox = t.x0 + tx;
         const bool valid = oy < a.Ho && ox < a.Wo;
-        // element offset from the destination's base pointer; fits 32 bits (checked on the host); -1 = nothing to store
-        const int off = valid ? (int)(dst.off(t.n, oy, ox) + ch0) : -1;
+        // element offset inside image t.n of the destination; fits 32 bits (checked on the host); -1 = nothing to store
+        const int off = valid ? (int)(oy * dst.sh + ox * dst.sw + ch0) : -1;
+        const long long img = (long long)t.n * dst.sn;
         const uint32_t taddr = tmem_base + buf * (MB * BN) + mb * BN + lane_base;
         bf16* const dlo = a.dst_lo[d];
         // split tier: a second pass over the same accumulators writes the low-order plane (the TMEM read is repeated
@@ -442,7 +443,7 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
           }
           __syncwarp();
           // store side: lane (rsub, cch) moves chunk cch of rows rsub, rsub + RPI, ...
-          bf16* const dp = (plane ? dlo : dst.p) + cch * 8;
+          bf16* const dp = (plane ? dlo : dst.p) + img + cch * 8;
           const bool col_ok = t.n0 + col0 + cch * 8 < a.cout_total;
           int offs[LPR];
 #pragma unroll
@@ -452,7 +453,7 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
               bf16x8 mv[LPR];
 #pragma unroll
               for (int i = 0; i < LPR; ++i)
-                if (offs[i] >= 0) mv[i] = *reinterpret_cast<const bf16x8*>(mk + cch * 8 + offs[i]);
+                if (offs[i] >= 0) mv[i] = *reinterpret_cast<const bf16x8*>(mk + img + cch * 8 + offs[i]);
 #pragma unroll
               for (int i = 0; i < LPR; ++i) {
                 const int R = i * RPI + rsub;
@@ -513,8 +514,8 @@ struct Plan {
 };
 
 static bool aligned_view(const b200_view& v) {
-  // the epilogue addresses a destination with 32-bit element offsets from its base pointer
-  const int64_t span = (int64_t)(v.n - 1) * v.stride_n + (int64_t)(v.h - 1) * v.stride_h + (int64_t)(v.w - 1) * v.stride_w + v.c;
+  // the epilogue addresses a destination with 32-bit element offsets inside one image
+  const int64_t span = (int64_t)(v.h - 1) * v.stride_h + (int64_t)(v.w - 1) * v.stride_w + v.c;
   return v.c % 8 == 0 && reinterpret_cast<uintptr_t>(v.ptr) % 16 == 0 && reinterpret_cast<uintptr_t>(v.lo) % 16 == 0 &&
          v.stride_w % 8 == 0 && v.stride_h % 8 == 0 && (v.n == 1 || v.stride_n % 8 == 0) && span < (int64_t(1) << 31);
 }
