@@ -325,31 +325,34 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     // writes bias[n0 .. n0+BN) into the rows of accumulator buffer `buf` — each warp exactly the (M-block, column
     // pass) regions it drains itself, so a fast warp never overwrites a region its partner is still reading
     constexpr int PASSES = BN / CP;
+    // one (M-block, column pass) region: CP columns of bias for the tile whose N origin is n0
+    auto preload_item = [&](int n0, int buf, int mb, int c0) {
+#pragma unroll 1
+      for (int col0 = c0; col0 < c0 + CP; col0 += 32) {
+        // several destinations (ConvTranspose quadrants) share one bias vector: column -> channel inside its destination
+        const int nc = n0 + col0;
+        const int d = a.ndst > 1 ? min(nc / a.dst_c0, a.ndst - 1) : 0;
+        const float* bp = a.bias + (nc - d * a.dst_c0);
+        uint32_t bv[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (nc + 4 * j < a.cout_total) f = *reinterpret_cast<const float4*>(bp + 4 * j);
+          bv[4 * j] = __float_as_uint(f.x);
+          bv[4 * j + 1] = __float_as_uint(f.y);
+          bv[4 * j + 2] = __float_as_uint(f.z);
+          bv[4 * j + 3] = __float_as_uint(f.w);
+        }
+        tmem_st_32x32(tmem_base + buf * (MB * BN) + mb * BN + col0 + lane_base, bv);
+      }
+    };
     auto preload_bias = [&](int tile, int buf) {
       if (a.bias == nullptr) return;
       const TileCoord t = decode_tile<CL>(a, tile, rank, BN);
 #pragma unroll 1
       for (int wi = egrp; wi < MB * PASSES; wi += 2) {
         const int mb = wi / PASSES;
-        const int c0 = (wi - mb * PASSES) * CP;
-#pragma unroll 1
-        for (int col0 = c0; col0 < c0 + CP; col0 += 32) {
-          // several destinations (ConvTranspose quadrants) share one bias vector: column -> channel inside its destination
-          const int nc = t.n0 + col0;
-          const int d = a.ndst > 1 ? min(nc / a.dst_c0, a.ndst - 1) : 0;
-          const float* bp = a.bias + (nc - d * a.dst_c0);
-          uint32_t bv[32];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (nc + 4 * j < a.cout_total) f = *reinterpret_cast<const float4*>(bp + 4 * j);
-            bv[4 * j] = __float_as_uint(f.x);
-            bv[4 * j + 1] = __float_as_uint(f.y);
-            bv[4 * j + 2] = __float_as_uint(f.z);
-            bv[4 * j + 3] = __float_as_uint(f.w);
-          }
-          tmem_st_32x32(tmem_base + buf * (MB * BN) + mb * BN + col0 + lane_base, bv);
-        }
+        preload_item(t.n0, buf, mb, (wi - mb * PASSES) * CP);
       }
       tmem_st_wait();
     };
@@ -369,6 +372,12 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     for (int tile = work0; tile < total_tiles; tile += work_step, ++it) {
       const TileCoord t = decode_tile<CL>(a, tile, rank, BN);
       const int buf = it % NBUF;
+      // this buffer's next user is tile + NBUF * work_step: its bias is stored region by region, right after a region
+      // has been drained, so that the asynchronous tcgen05.st overlaps the rest of the epilogue (a single store + wait
+      // block at the end of the tile cost ~20 % of the epilogue warps' time on the 64-channel layers)
+      const int next = tile + NBUF * work_step;
+      const bool pre = a.bias != nullptr && next < total_tiles;
+      const int next_n0 = pre ? decode_tile<CL>(a, next, rank, BN).n0 : 0;
       mbar_wait(&t_full[buf], (it / NBUF) & 1);
       tc_fence_after_sync();
 #pragma unroll 1  // keep the epilogue body small: fully unrolled it was ~3000 instructions and ran out of the I-cache
@@ -478,10 +487,9 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
           }
           __syncwarp();
         }
+        if (pre) preload_item(next_n0, buf, mb, col0);  // this region is drained: store the next user's bias into it
       }
-      // this buffer's next user is tile + NBUF * work_step: pre-load its bias, then hand the buffer back
-      const int next = tile + NBUF * work_step;
-      if (next < total_tiles) preload_bias(next, buf);
+      if (pre) tmem_st_wait();  // the bias stores issued along the way; then hand the buffer back
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) {
