@@ -99,6 +99,7 @@ __device__ __forceinline__ TileCoord decode_tile(const UmmaArgs& a, int work, in
   return t;
 }
 
+// 168 registers is the ceiling for 11 warps: an SM sub-partition (16384 registers) hosts three of them
 template <int MB, int BN, int CL>
 __global__ void __launch_bounds__(kUmmaThreads, 1)
 umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ UmmaArgs a) {
