@@ -242,6 +242,29 @@ def test_eval_forward_reuses_packed_weights_and_sees_updates():
     assert rel_l2(o4.cpu(), ref4) < TOL_LOGITS
 
 
+def test_ragged_and_degenerate_inputs():
+    """Odd extents (pooling floors, the up path is smaller than the bridge and the crop is off-centre by the reference's
+    integer division, unet.py:152-158), a batch of one, and an input too small for the valid convolutions."""
+    spec = O.UNetSpec(3, 3, 3, 4, True, False, "upconv")
+    sd = O.init_params(spec, seed=4)
+    model = build(spec.__dict__).cuda()
+    model.load_state_dict(sd)
+    for (n, h, w) in [(1, 37, 51), (2, 29, 30), (1, 8, 9)]:
+        torch.manual_seed(h)
+        x = torch.randn(n, 3, h, w)
+        ho, wo = O.output_hw(spec, h, w)
+        y = torch.randint(0, 3, (n, ho, wo))
+        ref_logits, ref_loss, ref_grads, _ = O.loss_and_grads(sd, x, y, spec)
+        logits, loss, grads = run_step(model, x.cuda(), y.cuda(), fused_loss=False)
+        assert logits.shape == ref_logits.shape
+        assert rel_l2(logits, ref_logits) <= TOL_LOGITS
+        eg, _, _ = grad_errors(grads, ref_grads)
+        assert eg <= TOL_GRAD, (n, h, w, eg)
+    valid = build(O.UNetSpec(1, 2, 3, 4, False, False, "upconv").__dict__).cuda()
+    with pytest.raises(RuntimeError):
+        valid(torch.randn(1, 1, 12, 12, device="cuda"))   # 12 -> 8 -> 4 -> 0: nothing left for the third block
+
+
 def test_two_forwards_then_backward():
     """The repo's own trainer runs the U-Net on both images of a pair before backward (network_modules.py:123-132)."""
     spec = O.UNetSpec(1, 2, 2, 3, False, False, "upconv")
