@@ -152,3 +152,26 @@ def test_cuda_graph_step_with_fused_adam():
     graphed = [float(step(x, y)) for _ in range(3)]   # warm-up ran steps 0..2, the capture itself does not execute
     for a, b in zip(graphed, eager[3:]):
         assert abs(a - b) <= 2e-3 * max(1.0, abs(b)), (graphed, eager)
+
+
+def test_training_converges_on_a_learnable_task():
+    """Paper graph (wf = 5 so that the CTA-pair kernels take part), learnable synthetic task, FusedAdam: the loss must
+    fall well below log(2) — an end-to-end check that forward, backward and the optimizer agree with each other."""
+    import b200unet
+    torch.manual_seed(0)
+    m = b200unet.UNet(1, 2, 4, 5, False, False, "upconv").cuda().train()
+    opt = b200unet.FusedAdam(m.parameters(), lr=3e-4, model=m)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    first = last = None
+    for it in range(120):
+        x = torch.randn(4, 1, 188, 188, device="cuda", generator=g)
+        sm = F.avg_pool2d(x, 5, stride=1, padding=2)
+        ho = 188 - 88
+        y = (sm[:, 0, 44:44 + ho, 44:44 + ho] > 0).long()
+        loss = m.loss(x, y)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        last = float(loss.detach())
+        first = last if first is None else first
+    assert abs(first - 0.693) < 0.05 and last < 0.45, (first, last)
