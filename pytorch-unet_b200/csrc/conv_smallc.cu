@@ -42,11 +42,11 @@ smallc_fwd_kernel(DView src, DView dst, const float* __restrict__ w, const float
   const int oy = (int)(t2 % dst.h), n = (int)(t2 / dst.h);
   const int ox0 = xg * 4;
 
-  float acc[4][16];
+  float2 acc[4][8];  // 4 pixels x 16 channels as fp32 pairs: FFMA2 does two channels per instruction
 #pragma unroll
   for (int p = 0; p < 4; ++p)
 #pragma unroll
-    for (int k = 0; k < 16; ++k) acc[p][k] = 0.f;
+    for (int k = 0; k < 8; ++k) acc[p][k] = make_float2(0.f, 0.f);
 
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
@@ -72,12 +72,12 @@ smallc_fwd_kernel(DView src, DView dst, const float* __restrict__ w, const float
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
           const float4 wv = *reinterpret_cast<const float4*>(wp + j4 * 4);
+          const float2 w01 = make_float2(wv.x, wv.y), w23 = make_float2(wv.z, wv.w);
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
-            acc[p][j4 * 4 + 0] += xin[p + s] * wv.x;
-            acc[p][j4 * 4 + 1] += xin[p + s] * wv.y;
-            acc[p][j4 * 4 + 2] += xin[p + s] * wv.z;
-            acc[p][j4 * 4 + 3] += xin[p + s] * wv.w;
+            const float2 xx = make_float2(xin[p + s], xin[p + s]);
+            acc[p][j4 * 2 + 0] = ffma2(xx, w01, acc[p][j4 * 2 + 0]);
+            acc[p][j4 * 2 + 1] = ffma2(xx, w23, acc[p][j4 * 2 + 1]);
           }
         }
       }
@@ -90,7 +90,7 @@ smallc_fwd_kernel(DView src, DView dst, const float* __restrict__ w, const float
     float f[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      f[k] = acc[p][k] + bs[q4 * 16 + k];
+      f[k] = ((k & 1) ? acc[p][k >> 1].y : acc[p][k >> 1].x) + bs[q4 * 16 + k];
       if (relu) f[k] = fmaxf(f[k], 0.f);
     }
     const long long oo = dst.off(n, oy, ox) + o_base + q4 * 16;
