@@ -1,7 +1,7 @@
 """BASELINE.json configurations at their FULL sizes on the B200 (through the drop-in module -> C ABI).
 
 config 1 (paper default, batch 1, 572x572) is small enough for the CPU oracle: logits / loss / gradients are compared
-against it with north_star's tolerances; so are the two BatchNorm configurations (2 and 5, full batch: the batch
+against it with north_star's tolerances; so is config 4 at its 1024x1024 resolution with one image, and so are the two BatchNorm configurations (2 and 5, full batch: the batch
 statistics are part of the result), which run in the module's split precision tier.  For the larger configurations the
 oracle would take minutes, so they are checked through size-independent properties of the training step:
   * run-to-run bit-exactness (every kernel reduces in a fixed order),
@@ -62,6 +62,32 @@ def test_config1_paper_default_batch1_572_vs_oracle():
     print(f"[config1 572^2] logits rel-L2 {e:.3e} argmax agreement {agree:.5f} grad rel-L2 {eg:.3e} "
           f"loss {float(loss):.6f} vs {float(ref_loss):.6f}")
     assert e <= 1e-2 and eg <= 2e-2 and agree >= 0.999   # BASELINE.json north_star tolerances
+    assert abs(float(loss) - float(ref_loss)) <= 1e-3 * max(1.0, abs(float(ref_loss)))
+
+
+def test_config4_full_resolution_batch1_vs_oracle():
+    """BASELINE config 4 (in=3, depth 4, wf 5, same padding) at its full 1024x1024 resolution, one image (the oracle
+    needs ~20 s of CPU for it): 32-channel layers, zero padding at every level, the widest tensors of all configs."""
+    import b200unet
+    spec = O.UNetSpec(3, 2, 4, 5, True, False, "upconv")
+    sd = O.init_params(spec, seed=0)
+    torch.manual_seed(3)
+    x = torch.randn(1, 3, 1024, 1024)
+    y = (x[:, 0] > 0).long()
+    ref_logits, ref_loss, ref_grads, _ = O.loss_and_grads(sd, x, y, spec)
+    model = b200unet.UNet(3, 2, 4, 5, True, False, "upconv").cuda().train()
+    model.load_state_dict(sd)
+    logits = model(x.cuda())
+    loss = F.cross_entropy(logits, y.cuda())
+    loss.backward()
+    e = rel_l2(logits.detach().cpu(), ref_logits)
+    agree = float((logits.argmax(1).cpu() == ref_logits.argmax(1)).float().mean())
+    keys = list(ref_grads)
+    eg = rel_l2(torch.cat([dict(model.named_parameters())[k].grad.cpu().flatten() for k in keys]),
+                torch.cat([ref_grads[k].flatten() for k in keys]))
+    print(f"[config4 1024^2 b1] logits rel-L2 {e:.3e} argmax agreement {agree:.5f} grad rel-L2 {eg:.3e} "
+          f"loss {float(loss):.6f} vs {float(ref_loss):.6f}")
+    assert e <= 1e-2 and eg <= 2e-2 and agree >= 0.999
     assert abs(float(loss) - float(ref_loss)) <= 1e-3 * max(1.0, abs(float(ref_loss)))
 
 
