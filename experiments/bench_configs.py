@@ -22,7 +22,7 @@ for name, cfg in CFG.items():
 for name, (args, ub, b, h, w), tier in RUNS:
     torch.manual_seed(0)
     m = b200unet.UNet(*args, up_block=ub, precision=tier).cuda().train()
-    opt = torch.optim.Adam(m.parameters(), lr=1e-4, fused=True)
+    opt = b200unet.FusedAdam(m.parameters(), lr=1e-4, model=m)
     spec = O.UNetSpec(*args[:7], non_neg=(args[7] if len(args) > 7 else False), up_block=ub)
     ho, wo = O.output_hw(spec, h, w)
     x = torch.randn(b, args[0], h, w, device="cuda")

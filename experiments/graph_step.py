@@ -17,7 +17,7 @@ for name in sys.argv[1:] or ["config5"]:
     args, ub, b, h, w = CFG[name]
     torch.manual_seed(0)
     m = b200unet.UNet(*args, up_block=ub).cuda().train()
-    opt = torch.optim.Adam(m.parameters(), lr=1e-4, capturable=True, fused=True)
+    opt = b200unet.FusedAdam(m.parameters(), lr=1e-4, model=m)
     spec = O.UNetSpec(*args[:7], non_neg=(args[7] if len(args) > 7 else False), up_block=ub)
     ho, wo = O.output_hw(spec, h, w)
     x = torch.randn(b, args[0], h, w, device="cuda")
