@@ -209,9 +209,12 @@ int b200unet_bn_fwd_train(const b200_view* x, const b200_view* y, const float* g
 int b200unet_bn_fwd_eval(const b200_view* x, const b200_view* y, const float* gamma, const float* beta,
                          const float* running_mean, const float* running_var, float eps, void* stream);
 /* dx = gamma*invstd*(dy - mean(dy) - xhat*mean(dy*xhat)) [* (x > 0): ReLU backward of the conv before it];
- * dgamma / dbeta fp32 [c].  x is the BN input (post-ReLU activation).                                     */
+ * dgamma / dbeta fp32 [c].  x is the BN input (post-ReLU activation).
+ * flags: bit 0 = apply the ReLU mask (x > 0); bit 1 = save_mean / save_invstd are constants (eval mode: running_mean and
+ * rsqrt(running_var + eps)), i.e. dx = gamma*invstd*dy — torch's BatchNorm backward with training=False.            */
+enum { B200_BN_RELU_MASK = 1, B200_BN_FROZEN_STATS = 2 };
 int b200unet_bn_bwd(const b200_view* x, const b200_view* dy, const b200_view* dx, const float* gamma,
-                    const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, int relu_mask,
+                    const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, int flags,
                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- head: 1x1 conv to n_classes (<= 8) [+ReLU]; logits fp32 NCHW (the module's return value).

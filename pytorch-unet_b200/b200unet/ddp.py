@@ -35,11 +35,17 @@ class GradBucketer:
     can be exercised on CPU with the gloo backend."""
 
     def __init__(self, names: Sequence[str], shapes: Dict[str, Tuple[int, ...]], bucket_bytes: int = 32 << 20,
-                 process_group=None, average: bool = True):
+                 process_group=None, average: bool = True, grad_dtype: str = "fp32"):
+        assert grad_dtype in ("fp32", "bf16")
+        self.grad_dtype = grad_dtype  # wire precision of the all-reduce (the arena and the optimizer stay fp32)
+        self.profile = False          # bench.py: measure how long the end of backward waits for the collectives
+        self._prof: List[Tuple[torch.cuda.Event, torch.cuda.Event]] = []
         self.names = list(names)
         self.shapes = dict(shapes)
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        # ReduceOp.AVG exists in NCCL only; other backends (gloo: CPU tests, single-GPU multi-process tests) sum and divide
+        self._nccl = dist.is_initialized() and dist.get_backend(process_group) == "nccl"
         self.average = average
         self.offsets: Dict[str, Tuple[int, int]] = {}
         self.bucket_of: Dict[str, int] = {}
@@ -88,32 +94,61 @@ class GradBucketer:
             return
         s, e, _ = self.buckets[b]
         buf = self.arena[s:e]
-        if self.average and buf.is_cuda:
-            self._handles.append((dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.pg, async_op=True), None))
+        if self.grad_dtype == "bf16" and buf.is_cuda and self._nccl:
+            # half the bytes on the wire: the bucket travels as bf16 and is widened back after the reduction
+            wire = buf.to(torch.bfloat16)
+            h = dist.all_reduce(wire, op=dist.ReduceOp.AVG if self.average else dist.ReduceOp.SUM, group=self.pg,
+                                async_op=True)
+            self._handles.append((h, None, (buf, wire)))
+        elif self.average and buf.is_cuda and self._nccl:
+            self._handles.append((dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.pg, async_op=True), None, None))
         else:
             h = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
-            self._handles.append((h, buf if self.average else None))
+            self._handles.append((h, buf if self.average else None, None))
 
     def finish(self) -> None:
-        for h, scale_buf in self._handles:
+        prof = self.profile and self._handles and self.arena is not None and self.arena.is_cuda \
+            and not torch.cuda.is_current_stream_capturing()
+        if prof:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        for h, scale_buf, widen in self._handles:
             h.wait()
             if scale_buf is not None:
                 scale_buf.div_(self.world)
+            if widen is not None:
+                widen[0].copy_(widen[1])
+        if prof:
+            e1.record()
+            self._prof.append((e0, e1))
         self._handles = []
         self.arena = None  # the views handed out keep the storage alive
+
+    def profile_summary(self) -> dict:
+        """Mean time per step the compute stream spent waiting for outstanding all-reduces at the end of backward
+        (the part of the collective that did NOT overlap), from CUDA events on the compute stream."""
+        if not self._prof:
+            return {"buckets": len(self.buckets), "bucket_mb": [round((e - s) * 4 / 2 ** 20, 2) for s, e, _ in self.buckets]}
+        torch.cuda.synchronize()
+        waits = [a.elapsed_time(b) for a, b in self._prof]
+        self._prof = []
+        return {"exposed_allreduce_wait_ms": sum(waits) / len(waits), "max_ms": max(waits), "steps": len(waits),
+                "buckets": len(self.buckets), "bucket_mb": [round((e - s) * 4 / 2 ** 20, 2) for s, e, _ in self.buckets],
+                "grad_dtype": self.grad_dtype}
 
 
 class DataParallel(torch.nn.Module):
     """`DataParallel(UNet(...).cuda())`: same call surface as the wrapped module (`forward`, `loss`)."""
 
-    def __init__(self, module, bucket_bytes: int = 32 << 20, process_group=None, broadcast: bool = True):
+    def __init__(self, module, bucket_bytes: int = 32 << 20, process_group=None, broadcast: bool = True,
+                 grad_dtype: str = "fp32"):
         super().__init__()
         self.module = module
         if dist.is_initialized() and broadcast:
             for t in list(module.parameters()) + list(module.buffers()):
                 dist.broadcast(t.data, src=0, group=process_group)
         shapes = {n: tuple(p.shape) for n, p in module.named_parameters()}
-        self.bucketer = GradBucketer(backward_order(module), shapes, bucket_bytes, process_group)
+        self.bucketer = GradBucketer(backward_order(module), shapes, bucket_bytes, process_group, grad_dtype=grad_dtype)
         module._grad_alloc = self.bucketer.alloc
         module._grad_ready = self.bucketer.ready
         module._grads_done = self.bucketer.finish

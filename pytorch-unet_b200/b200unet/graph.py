@@ -25,8 +25,11 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
+        from . import _lib
+        n0 = _lib.load().b200unet_launch_count()
         with torch.cuda.graph(self.graph):
             self.loss = self._step()
+        self.launches_per_replay = int(_lib.load().b200unet_launch_count() - n0)  # kernels of this library in the graph
 
     def _step(self) -> torch.Tensor:
         loss = self.model.loss(self.x, self.y)
@@ -39,4 +42,9 @@ class GraphedTrainStep:
         self.x.copy_(x, non_blocking=True)
         self.y.copy_(y, non_blocking=True)
         self.graph.replay()
+        # the replay updated the weights without running any Python of the module: bf16 operand copies an eval-mode
+        # forward made earlier are stale now (UNet._packed reuses them only within one value of this counter)
+        m = getattr(self.model, "module", self.model)
+        if hasattr(m, "_train_forwards"):
+            m._train_forwards += 1
         return self.loss

@@ -16,6 +16,8 @@ from ._lib import (IMPL_AUTO, IMPL_DIRECT, IMPL_UMMA, ConvDgradParams, ConvFwdPa
 
 __all__ = ["IMPL_AUTO", "IMPL_DIRECT", "IMPL_UMMA", "Split", "hi_of"]
 
+MAX_CLASSES = 8  # head / loss kernels: one accumulator per class in registers (csrc/head.cu)
+
 _workspaces = {}
 
 
@@ -41,13 +43,19 @@ def _nhwc_empty(n, h, w, c, device, split: bool = False):
 
 
 # ------------------------------------------------------------------ layout
-def to_nhwc(x: torch.Tensor, split: bool = False):
-    """fp32 NCHW (module input, unet.py:73) -> bf16 NHWC (hi/lo pair in the split tier)."""
+def to_nhwc(x: torch.Tensor, split: bool = False, c_pad: Optional[int] = None):
+    """fp32 NCHW (module input, unet.py:73) -> bf16 NHWC (hi/lo pair in the split tier).  c_pad > C: the result has
+    c_pad channels, the extra ones zero."""
     assert x.dim() == 4 and x.dtype == torch.float32 and x.is_cuda
     x = x.contiguous()
     n, c, h, w = x.shape
-    y = _nhwc_empty(n, h, w, c, x.device, split)
-    v = view(y)
+    if c_pad is not None and c_pad > c:
+        hi = torch.zeros((n, h, w, c_pad), dtype=torch.bfloat16, device=x.device)
+        y = Split(hi, torch.zeros_like(hi)) if split else hi
+        v = view(y[..., :c])
+    else:
+        y = _nhwc_empty(n, h, w, c, x.device, split)
+        v = view(y)
     check(_lib.load().b200unet_nchw_f32_to_nhwc_bf16(x.data_ptr(), C.byref(v), stream_ptr()), "nchw_f32_to_nhwc_bf16")
     return y
 
@@ -292,7 +300,9 @@ def bn_fwd_eval(x, gamma, beta, running_mean, running_var, eps: float):
     return y
 
 
-def bn_bwd(x, dy, gamma, mean, invstd, relu_mask: bool, dx=None, dgamma=None, dbeta=None):
+def bn_bwd(x, dy, gamma, mean, invstd, relu_mask: bool, dx=None, dgamma=None, dbeta=None, frozen_stats: bool = False):
+    """BatchNorm2d backward (+ ReLU mask of the conv in front).  frozen_stats: `mean` / `invstd` are the running
+    statistics of an eval-mode forward (torch's batch_norm backward with training=False)."""
     lib = _lib.load()
     c = x.shape[3]
     if dx is None:
@@ -304,7 +314,8 @@ def bn_bwd(x, dy, gamma, mean, invstd, relu_mask: bool, dx=None, dgamma=None, db
     ws = workspace(lib.b200unet_bn_workspace_bytes(c), x.device)
     vx, vdy, vdx = view(x), view(dy), view(dx)
     check(lib.b200unet_bn_bwd(C.byref(vx), C.byref(vdy), C.byref(vdx), gamma.data_ptr(), mean.data_ptr(),
-                              invstd.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), int(relu_mask), ws.data_ptr(),
+                              invstd.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), int(relu_mask) | (2 if frozen_stats else 0),
+                              ws.data_ptr(),
                               ws.numel(), stream_ptr()), "bn_bwd")
     return dx, dgamma, dbeta
 

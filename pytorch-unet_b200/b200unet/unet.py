@@ -99,10 +99,12 @@ class _UNetFunction(torch.autograd.Function):
     def forward(ctx, model: "UNet", x: torch.Tensor, labels: Optional[torch.Tensor], *params: torch.Tensor):
         names = model._param_names
         P = dict(zip(names, params))
-        keep = any(ctx.needs_input_grad[3:])  # False under no_grad / frozen parameters
+        keep = ctx.needs_input_grad[1] or any(ctx.needs_input_grad[3:])  # False under no_grad / nothing requires grad
         tape = _Tape() if keep else None
         out = model._run_forward(x, labels, P, tape)
         ctx.model, ctx.tape, ctx.P, ctx.labels = model, tape, P, labels
+        ctx.want_dx = bool(ctx.needs_input_grad[1])
+        ctx.x_dtype = x.dtype
         ctx.set_materialize_grads(False)
         return out
 
@@ -114,8 +116,11 @@ class _UNetFunction(torch.autograd.Function):
         ctx.tape = None
         if grad_out is None:
             return (None, None, None) + tuple(None for _ in model._param_names)
-        grads = model._run_backward(tape, ctx.P, ctx.labels, grad_out)
-        return (None, None, None) + tuple(grads.get(n) for n in model._param_names)
+        grads = model._run_backward(tape, ctx.P, ctx.labels, grad_out, want_dx=ctx.want_dx)
+        dx = grads.pop("__input__", None)
+        if dx is not None and dx.dtype != ctx.x_dtype:
+            dx = dx.to(ctx.x_dtype)
+        return (None, dx, None) + tuple(grads.get(n) for n in model._param_names)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -126,8 +131,9 @@ class UNet(nn.Module):
 
     Positional arguments are the reference's (unet.py:9-19): in_channels, n_classes, depth, wf, padding, batch_norm,
     up_mode, non_neg.  `up_block` selects the decoder: 'paper' = UNetUpBlock (the graph of unet_original.py, the
-    7-argument signature in README.md:14-15) or 'deep' = UNetUpBlockDeep (what unet.py:60 builds).  Output: fp32
-    NCHW logits, differentiable w.r.t. the parameters.
+    7-argument signature in README.md:14-15) or 'deep' = UNetUpBlockDeep (what unet.py:60 builds); by default it is
+    'deep' exactly when the 8th argument `non_neg` is given (the call network_modules.py:73 makes), else 'paper'.
+    Output: fp32 NCHW logits, differentiable w.r.t. the parameters and the input.
 
     `precision` selects how forward activations and conv operands are carried: 'bf16' (one bf16 plane, one tensor-core
     pass) or 'split' (hi + lo bf16 planes, three passes, ~16 mantissa bits; the backward pass is the same bf16 one in
@@ -137,12 +143,21 @@ class UNet(nn.Module):
     """
 
     def __init__(self, in_channels: int = 1, n_classes: int = 2, depth: int = 5, wf: int = 6, padding: bool = False,
-                 batch_norm: bool = False, up_mode: str = "upconv", non_neg: bool = False, up_block: str = "paper",
-                 conv_impl: int = ops.IMPL_AUTO, precision: str = "auto"):
+                 batch_norm: bool = False, up_mode: str = "upconv", non_neg: Optional[bool] = None,
+                 up_block: Optional[str] = None, conv_impl: int = ops.IMPL_AUTO, precision: str = "auto"):
         super().__init__()
         assert up_mode in ("upconv", "upsample")  # unet.py:45
+        if up_block is None:
+            # Only unet.py's UNet has the 8th argument, and that class always builds UNetUpBlockDeep (unet.py:60): a
+            # call that passes `non_neg` (network_modules.py:73 does, positionally) gets that graph, so its checkpoints
+            # load.  The 7-argument signature of README.md:14-15 / unet_original.py builds the paper decoder.
+            up_block = "deep" if non_neg is not None else "paper"
+        non_neg = bool(non_neg)
         assert up_block in ("paper", "deep")
         assert precision in ("auto", "bf16", "split")
+        if not 1 <= n_classes <= ops.MAX_CLASSES:
+            raise ValueError(f"b200unet.UNet: n_classes must be in 1..{ops.MAX_CLASSES} (the fused classifier / loss "
+                             f"kernels keep one accumulator per class in registers), got {n_classes}")
         self.precision = ("split" if batch_norm else "bf16") if precision == "auto" else precision
         self.padding = padding
         self.depth = depth
@@ -191,6 +206,22 @@ class UNet(nn.Module):
         self._pack_cache.clear()
         return super()._apply(fn, *args, **kwargs)
 
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        """nn.Module.load_state_dict, plus a clear message when the checkpoint belongs to the other decoder variant: the
+        two are told apart by the shape of the first up-sampling weight ([C, C/2, ..] paper vs [C, C, ..] Deep)."""
+        for key in ("up_path.0.up.weight", "up_path.0.up.1.weight"):
+            mine = dict(self.named_parameters()).get(key)
+            theirs = state_dict.get(key) if hasattr(state_dict, "get") else None
+            if mine is not None and theirs is not None and tuple(mine.shape) != tuple(theirs.shape) \
+                    and mine.shape[0] != mine.shape[1] and theirs.shape[0] == theirs.shape[1] and self.up_block == "paper":
+                raise RuntimeError("b200unet.UNet: this checkpoint is from the UNetUpBlockDeep graph that unet.py builds "
+                                   "(unet.py:60); construct the module with up_block='deep' (or with the 8-argument call)")
+            if mine is not None and theirs is not None and tuple(mine.shape) != tuple(theirs.shape) \
+                    and mine.shape[0] == mine.shape[1] and theirs.shape[0] != theirs.shape[1] and self.up_block == "deep":
+                raise RuntimeError("b200unet.UNet: this checkpoint is from the paper decoder (unet_original.py / "
+                                   "UNetUpBlock); construct the module with up_block='paper' (or the 7-argument call)")
+        return super().load_state_dict(state_dict, strict=strict, **kw)
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return self._apply_fn(x, None)
 
@@ -216,12 +247,19 @@ class UNet(nn.Module):
     def _cpad(c: int) -> int:
         return c if (c % 8 == 0 and c >= 16) else max(16, (c + 7) // 8 * 8)
 
+    @staticmethod
+    def _cpad_image(c: int) -> int:
+        """Channel count the image is carried with: 1..4 channels go to the first-layer CUDA-core kernels as they are;
+        5, 6, 7, 9, ... are zero-padded to a multiple of 8 so that the tensor-core kernels take the first layer (the
+        reference accepts any in_channels, unet.py:49-52)."""
+        return c if (c <= 4 or c % 8 == 0) else (c + 7) // 8 * 8
+
     def _build_padspec(self, in_channels, n_classes, depth, wf):
         spec: Dict[str, tuple] = {}
         cp = self._cpad
 
         def conv(name, srcs_real, cout, pad_src=True):
-            srcs_pad = [cp(c) if pad_src else c for c in srcs_real]
+            srcs_pad = [cp(c) if pad_src else self._cpad_image(c) for c in srcs_real]
             segs, ro, po = [], 0, 0
             for r, pd in zip(srcs_real, srcs_pad):
                 segs.append((ro, r, po))
@@ -315,9 +353,13 @@ class UNet(nn.Module):
         else:
             src_c = list(src_c) if src_c is not None else [w.shape[1]]
             packed = ops.pack_conv_weight(w.detach(), src_c, mode, out=out)
-        self._pack_cache[key] = {"version": w._version, "ptr": w.data_ptr(), "tensor": packed, "mode": mode,
-                                 "src_c": src_c, "transposed": transposed_conv, "stamped": False,
-                                 "eval_epoch": self._train_forwards if not self.training else -1}
+        new = {"version": w._version, "ptr": w.data_ptr(), "tensor": packed, "mode": mode,
+               "src_c": src_c, "transposed": transposed_conv, "stamped": False,
+               "eval_epoch": self._train_forwards if not self.training else -1}
+        if e is not None:
+            e.update(new)  # in place: FusedAdam keeps references to the entries it stamps
+        else:
+            self._pack_cache[key] = new
         return packed
 
     def _new_grad(self, name: str, like: torch.Tensor) -> torch.Tensor:
@@ -384,7 +426,10 @@ class UNet(nn.Module):
                     rec[f"bn{i}"] = (mean, invstd)
                 else:
                     o = ops.bn_fwd_eval(a, g, bt, rm, rv, bn.eps)
-                    rec[f"bn{i}"] = None
+                    # backward through frozen statistics (fine-tuning in eval mode): torch's BatchNorm backward with
+                    # training=False, i.e. mean / invstd are constants
+                    rec[f"bn{i}"] = (rm, torch.rsqrt(rv + bn.eps)) if tape is not None else None
+                    rec[f"bn{i}_frozen"] = True
             else:
                 o = a
             rec[f"o{i}"] = ops.hi_of(o)
@@ -401,7 +446,7 @@ class UNet(nn.Module):
             tape.P = P
         if x.dtype != torch.float32:
             x = x.float()
-        cur = ops.to_nhwc(x, split=self.precision == "split")
+        cur = ops.to_nhwc(x, split=self.precision == "split", c_pad=self._cpad_image(x.shape[1]))
         bridges = []
         last_act = None
         for i, down in enumerate(self.down_path):
@@ -456,7 +501,8 @@ class UNet(nn.Module):
                 gam = P[bn_names[i] + ".weight"]
                 dgam = self._new_grad(bn_names[i] + ".weight", gam)
                 dbet = self._new_grad(bn_names[i] + ".bias", gam)
-                dz, _, _ = ops.bn_bwd(a, g, gam.detach(), mean, invstd, True, dx=g, dgamma=dgam, dbeta=dbet)
+                dz, _, _ = ops.bn_bwd(a, g, gam.detach(), mean, invstd, True, dx=g, dgamma=dgam, dbeta=dbet,
+                                      frozen_stats=rec.get(f"bn{i}_frozen", False))
                 grads[bn_names[i] + ".weight"], grads[bn_names[i] + ".bias"] = dgam, dbet
             else:
                 dz = g
@@ -481,12 +527,20 @@ class UNet(nn.Module):
                 ops.conv_dgrad(dz, w.detach(), pad, [g], [None if blk.batch_norm else rec["a0"]], impl=self.conv_impl,
                                w_packed=lambda: self._packed(names[i] + ".weight", w, 1))
             elif src_dsts is not None:
-                ops.conv_dgrad(dz, w.detach(), pad, src_dsts, src_masks, impl=self.conv_impl,
-                               w_packed=lambda: self._packed(names[i] + ".weight", w, 1))
+                cin_dst = sum(d.shape[3] for d in src_dsts)
+                if cin_dst != w.shape[1]:
+                    # gradient w.r.t. the image (unet.py:73-84 is differentiable in x): the 1..4-channel image gradient is
+                    # produced with its channels zero-padded to 8, which is what the tensor-core kernel can store
+                    wp = torch.zeros((w.shape[0], cin_dst, w.shape[2], w.shape[3]), dtype=w.dtype, device=w.device)
+                    wp[:, :w.shape[1]] = w.detach()
+                    ops.conv_dgrad(dz, wp, pad, src_dsts, src_masks, impl=self.conv_impl)
+                else:
+                    ops.conv_dgrad(dz, w.detach(), pad, src_dsts, src_masks, impl=self.conv_impl,
+                                   w_packed=lambda: self._packed(names[i] + ".weight", w, 1))
             self._done(*( [bn_names[i] + ".weight", bn_names[i] + ".bias"] if blk.batch_norm else [] ),
                        names[i] + ".weight", names[i] + ".bias")
 
-    def _run_backward(self, tape, P, labels, grad_out) -> Dict[str, torch.Tensor]:
+    def _run_backward(self, tape, P, labels, grad_out, want_dx: bool = False) -> Dict[str, torch.Tensor]:
         P = tape.P
         grads: Dict[str, torch.Tensor] = {}
         self._cur_grads = grads
@@ -553,7 +607,13 @@ class UNet(nn.Module):
                 add = gb[:, dy:dy + wh, dx:dx + ww, :]
                 ops.maxpool_bwd(g, pool["idx8"], gb, add=add, add_y=dy, add_x=dx, mask=None if bn else pool["act"])
                 g = gb
-            if i == 0:
+            if i == 0 and want_dx:
+                ximg = tape.blocks["down_path.0"]["srcs"][0]
+                gx = torch.empty(tuple(ximg.shape[:3]) + (max(8, (ximg.shape[3] + 7) // 8 * 8),), dtype=torch.bfloat16,
+                                 device=g.device)
+                self._block_backward(f"down_path.{i}", down, tape, P, g, grads, [gx], [None])
+                grads["__input__"] = ops.to_nchw(gx)[:, :self.in_channels]
+            elif i == 0:
                 self._block_backward(f"down_path.{i}", down, tape, P, g, grads, None, None)
             else:
                 prev_pooled_shape = tape.blocks[f"down_path.{i}"]["srcs"][0].shape

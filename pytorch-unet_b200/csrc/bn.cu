@@ -207,7 +207,7 @@ int b200unet_bn_fwd_eval(const b200_view* x, const b200_view* y, const float* ga
 }
 
 int b200unet_bn_bwd(const b200_view* x, const b200_view* dy, const b200_view* dx, const float* gamma,
-                    const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, int relu_mask,
+                    const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, int flags,
                     void* workspace, size_t workspace_bytes, void* stream) {
   B200_REQUIRE(view_ok(x) && view_ok(dy) && view_ok(dx) && same_extent(*x, *dy) && same_extent(*x, *dx) && gamma &&
                    save_mean && save_invstd && dgamma && dbeta && workspace,
@@ -227,7 +227,10 @@ int b200unet_bn_bwd(const b200_view* x, const b200_view* dy, const b200_view* dx
   if (r) return r;
   const bool v8 = vec8_ok(*x) && vec8_ok(*dy) && vec8_ok(*dx);
   const long long total = view_pixels(*x) * (v8 ? x->c / 8 : x->c);
-  const float inv_count = 1.f / (float)view_pixels(*x);
+  // flags bit 1: mean / invstd are constants (eval mode: running statistics), so the batch-statistic correction terms
+  // of the training-mode formula vanish: dx = gamma * invstd * dy
+  const float inv_count = (flags & 2) ? 0.f : 1.f / (float)view_pixels(*x);
+  const int relu_mask = flags & 1;
   if (v8)
     bn_bwd_apply_kernel<8><<<stream_grid(total), 256, 0, st>>>(dview(*x), dview(*dy), dview(*dx), gamma, save_mean,
                                                               save_invstd, sums, inv_count, relu_mask);

@@ -150,10 +150,13 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadArgs a) {
     }
     if (MODE == HEAD_CE_FWD) {
       if (valid && lane8 == 0) {
+        // a label outside [0, K) that is not ignore_index is an error (F.cross_entropy raises a device-side assert):
+        // it poisons the loss with NaN instead of silently counting as some class
         float zy = 0.f;
 #pragma unroll
         for (int k = 0; k < KMAX; ++k)
           if (k == (int)label) zy = zr[k];
+        if (label < 0 || label >= K) zy = __int_as_float(0x7fc00000);
         loss_acc += lse - zy;
         cnt_acc += 1.f;
       }
