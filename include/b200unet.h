@@ -240,6 +240,12 @@ int b200unet_head_ce_bwd(const b200_view* x, const float* w, const float* b, int
 /* ---- boundary transforms */
 int b200unet_nchw_f32_to_nhwc_bf16(const float* src, const b200_view* dst, void* stream);
 int b200unet_nhwc_bf16_to_nchw_f32(const b200_view* src, float* dst, void* stream);
+/* Input pipeline (dataloader.py:258-264 image / 255, :553-579 ToTensor + per-sample upload): src is a dense uint8
+ * [n][h][w][src_c] batch (the layout image decoders produce) already on the device; dst (n, h, w as src, c >= src_c) receives
+ * dst[..., c] = (divide_255 ? src / 255 : src) * scale[c] + shift[c] as NHWC bf16 (both planes when dst->lo is set), zero in
+ * channels >= src_c.  scale / shift: fp32 [src_c] or NULL.  Replaces fp32 NCHW upload + nchw_f32_to_nhwc_bf16.            */
+int b200unet_u8_nhwc_to_bf16(const uint8_t* src, int src_c, const b200_view* dst, const float* scale, const float* shift,
+                             int divide_255, void* stream);
 /* First-layer helper: dst[n,y,x, c*9 + r*3 + s] = src[n, y+r-pad, x+s-pad, c] (zero outside and in the padding channels);
  * dst.c >= 9*src.c, multiple of 8.  Turns the 1..7-channel first convolution (unet.py:49-52) into a 1x1 problem so that it and
  * its backward-weights run on the tensor-core kernels. */

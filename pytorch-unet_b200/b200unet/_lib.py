@@ -109,6 +109,7 @@ SIGNATURES = {
     "b200unet_head_ce_bwd": (_I, [_VP, _P, _P, _I, _I, _P, _P, _P, _VP, _P, _P, _P, _P, _SZ, _P]),
     "b200unet_nchw_f32_to_nhwc_bf16": (_I, [_P, _VP, _P]),
     "b200unet_nhwc_bf16_to_nchw_f32": (_I, [_VP, _P, _P]),
+    "b200unet_u8_nhwc_to_bf16": (_I, [_P, _I, _VP, _P, _P, _I, _P]),
     "b200unet_im2col3x3": (_I, [_VP, _VP, _I, _P]),
     "b200unet_channel_sum": (_I, [_VP, _P, _P, _SZ, _P]),
     "b200unet_relu_mask": (_I, [_VP, _P, _VP, _P]),

@@ -60,6 +60,20 @@ def to_nhwc(x: torch.Tensor, split: bool = False, c_pad: Optional[int] = None):
     return y
 
 
+def u8_to_nhwc(img: torch.Tensor, split: bool = False, c_pad: Optional[int] = None, scale: Optional[torch.Tensor] = None,
+               shift: Optional[torch.Tensor] = None, divide_255: bool = True):
+    """uint8 [N,H,W,C] device batch -> the NHWC bf16 operand of the first convolution: img / 255 (dataloader.py:258-264)
+    [* scale + shift per channel], channels zero-padded to c_pad, hi/lo planes in the split tier."""
+    assert img.dim() == 4 and img.dtype == torch.uint8 and img.is_cuda and img.is_contiguous()
+    n, h, w, c = img.shape
+    cp = max(c, c_pad or c)
+    y = _nhwc_empty(n, h, w, cp, img.device, split)
+    v = view(y)
+    check(_lib.load().b200unet_u8_nhwc_to_bf16(img.data_ptr(), c, C.byref(v), ptr(scale), ptr(shift), int(divide_255),
+                                               stream_ptr()), "u8_nhwc_to_bf16")
+    return y
+
+
 def to_nchw(x: torch.Tensor) -> torch.Tensor:
     n, h, w, c = x.shape
     y = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)

@@ -22,6 +22,14 @@ import torch
 from torch import nn
 
 from . import ops
+from .input import PackedImages
+
+
+class _ImagesArg:
+    """Carries a PackedImages through torch.autograd.Function.apply (a non-tensor argument: no gradient)."""
+
+    def __init__(self, images: PackedImages):
+        self.images = images
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -104,7 +112,7 @@ class _UNetFunction(torch.autograd.Function):
         out = model._run_forward(x, labels, P, tape)
         ctx.model, ctx.tape, ctx.P, ctx.labels = model, tape, P, labels
         ctx.want_dx = bool(ctx.needs_input_grad[1])
-        ctx.x_dtype = x.dtype
+        ctx.x_dtype = getattr(x, "dtype", torch.float32)
         ctx.set_materialize_grads(False)
         return out
 
@@ -193,6 +201,7 @@ class UNet(nn.Module):
         self._grad_ready: Optional[Callable[[str], None]] = None
         self._grads_done: Optional[Callable[[], None]] = None
         self._pack_cache: Dict[Tuple[str, int], dict] = {}
+        self._nbt_pending: List[torch.Tensor] = []
         self._train_forwards = 0  # training-mode forwards so far: eval-mode packs are reused only within one value
 
     # ---------------------------------------------------------------- public API
@@ -233,6 +242,9 @@ class UNet(nn.Module):
     def _apply_fn(self, x, labels):
         if not x.is_cuda:
             raise RuntimeError("b200unet.UNet runs on CUDA (sm_100a) only: there is no CPU path")
+        if isinstance(x, PackedImages):  # b200unet.input: the batch is already the first convolution's operand
+            params = [p for _, p in self.named_parameters()]
+            return _UNetFunction.apply(self, _ImagesArg(x), labels, *params)
         params = [p for _, p in self.named_parameters()]
         return _UNetFunction.apply(self, x, labels, *params)
 
@@ -258,8 +270,9 @@ class UNet(nn.Module):
         spec: Dict[str, tuple] = {}
         cp = self._cpad
 
-        def conv(name, srcs_real, cout, pad_src=True):
-            srcs_pad = [cp(c) if pad_src else self._cpad_image(c) for c in srcs_real]
+        def conv(name, srcs_real, cout, pad_src=True, srcs_pad=None):
+            if srcs_pad is None:
+                srcs_pad = [cp(c) if pad_src else self._cpad_image(c) for c in srcs_real]
             segs, ro, po = [], 0, 0
             for r, pd in zip(srcs_real, srcs_pad):
                 segs.append((ro, r, po))
@@ -269,9 +282,9 @@ class UNet(nn.Module):
             if cp(cout) != cout:
                 spec[name + ".bias"] = ([(0, cout, 0)], cp(cout), None, None)
 
-        def block(prefix, srcs_real, cout, first=False):
+        def block(prefix, srcs_real, cout, first=False, srcs_pad=None):
             i2, b1, b2 = (3, 2, 5) if self.batch_norm else (2, None, None)
-            conv(f"{prefix}.block.0", srcs_real, cout, pad_src=not first)
+            conv(f"{prefix}.block.0", srcs_real, cout, pad_src=not first, srcs_pad=srcs_pad)
             conv(f"{prefix}.block.{i2}", [cout], cout)
             if self.batch_norm and cp(cout) != cout:
                 for b in (b1, b2):
@@ -285,14 +298,19 @@ class UNet(nn.Module):
         for j, i in enumerate(reversed(range(depth - 1))):
             skip = 2 ** (wf + i)
             up_out, blk_out = (skip, skip) if self.up_block == "paper" else (prev, prev)
+            up_pad = cp(up_out)
             if self.up_mode == "upconv":  # weight [cin, cout, 2, 2]
-                if cp(prev) != prev or cp(up_out) != up_out:
-                    spec[f"up_path.{j}.up.weight"] = ([(0, prev, 0)], cp(prev), [(0, up_out, 0)], cp(up_out))
-                if cp(up_out) != up_out:
-                    spec[f"up_path.{j}.up.bias"] = ([(0, up_out, 0)], cp(up_out), None, None)
+                if self.precision == "split" and up_pad % 32:
+                    # the transposed convolution of the split tier exists on the tensor-core kernel only, whose four
+                    # output quadrants must each be a whole number of 32-column epilogue passes
+                    up_pad = (up_pad + 31) // 32 * 32
+                if cp(prev) != prev or up_pad != up_out:
+                    spec[f"up_path.{j}.up.weight"] = ([(0, prev, 0)], cp(prev), [(0, up_out, 0)], up_pad)
+                if up_pad != up_out:
+                    spec[f"up_path.{j}.up.bias"] = ([(0, up_out, 0)], up_pad, None, None)
             else:
                 conv(f"up_path.{j}.up.1", [prev], up_out)
-            block(f"up_path.{j}.conv_block", [up_out, skip], blk_out)
+            block(f"up_path.{j}.conv_block", [up_out, skip], blk_out, srcs_pad=[up_pad, cp(skip)])
             prev = blk_out
         if cp(prev) != prev:
             spec[("last.0" if self.non_neg else "last") + ".weight"] = ([(0, n_classes, 0)], n_classes, [(0, prev, 0)], cp(prev))
@@ -422,7 +440,7 @@ class UNet(nn.Module):
                         bn.running_mean.copy_(rm[:bn.running_mean.numel()])
                         bn.running_var.copy_(rv[:bn.running_var.numel()])
                     if self.training and bn.num_batches_tracked is not None:
-                        bn.num_batches_tracked += 1
+                        self._nbt_pending.append(bn.num_batches_tracked)  # one fused increment per forward
                     rec[f"bn{i}"] = (mean, invstd)
                 else:
                     o = ops.bn_fwd_eval(a, g, bt, rm, rv, bn.eps)
@@ -439,14 +457,18 @@ class UNet(nn.Module):
         return cur[0], rec["a1"]
 
     def _run_forward(self, x, labels, P, tape):
+        self._nbt_pending = []
         if self.training:
             self._train_forwards += 1
         P = self._padded_params(P)
         if tape is not None:
             tape.P = P
-        if x.dtype != torch.float32:
-            x = x.float()
-        cur = ops.to_nhwc(x, split=self.precision == "split", c_pad=self._cpad_image(x.shape[1]))
+        if isinstance(x, _ImagesArg):
+            cur = x.images.data
+        else:
+            if x.dtype != torch.float32:
+                x = x.float()
+            cur = ops.to_nhwc(x, split=self.precision == "split", c_pad=self._cpad_image(x.shape[1]))
         bridges = []
         last_act = None
         for i, down in enumerate(self.down_path):
@@ -466,14 +488,20 @@ class UNet(nn.Module):
                 upv = ops.convt_fwd(cur, w, b, impl=self.conv_impl,
                                     w_packed=lambda: self._packed(wname, wparam, mode, transposed_conv=True))
             else:
-                u = ops.bilinear_fwd(cur)
-                rec["u"] = ops.hi_of(u)
-                upv = self._conv(f"up_path.{j}.up.1", [u], P, 0, relu=False)
+                # Sequential(Upsample(bilinear, x2), Conv2d 1x1) (unet.py:145-148, 175-178) evaluated as conv THEN
+                # upsample: a 1x1 convolution is per-pixel linear and the interpolation weights sum to one, so the two
+                # commute exactly (bias included; SURVEY.md 8c measured 2.4e-7 in fp32) — the GEMM runs on a quarter
+                # of the pixels and the full-resolution tensor is written once instead of written, read and written.
+                v = self._conv(f"up_path.{j}.up.1", [cur], P, 0, relu=False)
+                upv = ops.bilinear_fwd(v)
             win, dy, dx = _crop_window(bridge, upv.shape[1], upv.shape[2])
             rec.update({"crop": (dy, dx), "bridge_shape": bridge.shape, "up_shape": upv.shape})
             if tape is not None:
                 tape.ups.append(rec)
             cur, last_act = self._block_forward(f"up_path.{j}.conv_block", up.conv_block, [upv, win], P, tape)
+        if self._nbt_pending:  # BatchNorm2d.num_batches_tracked += 1 for every layer, as one multi-tensor launch
+            torch._foreach_add_(self._nbt_pending, 1)
+            self._nbt_pending = []
         hname = "last.0" if self.non_neg else "last"
         hw, hb = P[hname + ".weight"].detach(), P[hname + ".bias"].detach()
         hw2 = hw.view(hw.shape[0], hw.shape[1])
@@ -590,11 +618,13 @@ class UNet(nn.Module):
                 w = P[wn + ".weight"]
                 dw = self._new_grad(wn + ".weight", w)
                 db = self._new_grad(wn + ".bias", P[wn + ".bias"])
-                ops.conv_wgrad(d_up, [rec["u"]], 1, 0, impl=self.conv_impl, dw=dw, db=db)
-                gu = torch.empty_like(rec["u"])
-                ops.conv_dgrad(d_up, w.detach(), 0, [gu], [None], impl=self.conv_impl,
+                # reverse of conv-then-upsample: gradient back to low resolution first, 1x1 backward there
+                gv = torch.empty((xin.shape[0], xin.shape[1], xin.shape[2], d_up.shape[3]), dtype=torch.bfloat16,
+                                 device=g.device)
+                ops.bilinear_bwd(d_up, gv)
+                ops.conv_wgrad(gv, [xin], 1, 0, impl=self.conv_impl, dw=dw, db=db)
+                ops.conv_dgrad(gv, w.detach(), 0, [g], [xmask], impl=self.conv_impl,
                                w_packed=lambda: self._packed(wn + ".weight", w, 1))
-                ops.bilinear_bwd(gu, g, mask=xmask)
             grads[wn + ".weight"], grads[wn + ".bias"] = dw, db
             self._done(wn + ".weight", wn + ".bias")
             rec.clear()

@@ -31,7 +31,8 @@ smallc_fwd_kernel(DView src, DView dst, const float* __restrict__ w, const float
   const int q4 = threadIdx.x & 3;
   const int groups_per_row = (dst.w + 3) >> 2;
   const long long total_groups = (long long)dst.n * dst.h * groups_per_row;
-  if (o_base + q4 * 16 >= cout) return;
+  if (o_base + q4 * 8 >= cout) return;
+  const bool second_half = o_base + 32 + q4 * 8 < cout;  // cout is a multiple of 16, not necessarily of 64
   // grid-stride over pixel groups: the weights are staged once per block (one block per 256 pixels spent more time in
   // its prologue and in block scheduling than in the 576 FMAs per thread)
   for (long long pg = (long long)blockIdx.x * (kScThreads / 4) + (threadIdx.x >> 2); pg < total_groups;
@@ -68,10 +69,12 @@ smallc_fwd_kernel(DView src, DView dst, const float* __restrict__ w, const float
       }
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
-        const float* wp = ws + ((r * 3 + s) * CIN + c) * 64 + q4 * 16;
+        // lane q4 owns channels [8 q4, 8 q4 + 8) and [32 + 8 q4, 32 + 8 q4 + 8): the four lanes of a pixel then write two
+        // contiguous 64-byte runs (full 32-byte sectors per store instruction; 16 channels in a row per lane left gaps)
+        const float* wp = ws + ((r * 3 + s) * CIN + c) * 64 + q4 * 8;
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 wv = *reinterpret_cast<const float4*>(wp + j4 * 4);
+          const float4 wv = *reinterpret_cast<const float4*>(wp + (j4 >> 1) * 32 + (j4 & 1) * 4);
           const float2 w01 = make_float2(wv.x, wv.y), w23 = make_float2(wv.z, wv.w);
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
@@ -90,10 +93,10 @@ smallc_fwd_kernel(DView src, DView dst, const float* __restrict__ w, const float
     float f[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      f[k] = ((k & 1) ? acc[p][k >> 1].y : acc[p][k >> 1].x) + bs[q4 * 16 + k];
+      f[k] = ((k & 1) ? acc[p][k >> 1].y : acc[p][k >> 1].x) + bs[(k >> 3) * 32 + q4 * 8 + (k & 7)];
       if (relu) f[k] = fmaxf(f[k], 0.f);
     }
-    const long long oo = dst.off(n, oy, ox) + o_base + q4 * 16;
+    const long long oo = dst.off(n, oy, ox) + o_base + q4 * 8;
     float f0[8], f1[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -101,7 +104,7 @@ smallc_fwd_kernel(DView src, DView dst, const float* __restrict__ w, const float
       f1[k] = f[8 + k];
     }
     store8s(dst.p, dst.lo, oo, f0);
-    store8s(dst.p, dst.lo, oo + 8, f1);
+    if (second_half) store8s(dst.p, dst.lo, oo + 32, f1);
   }
   }
 }

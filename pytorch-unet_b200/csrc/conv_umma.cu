@@ -50,6 +50,7 @@ constexpr int kNA = 2;        // A (activation tile) stages
 constexpr int kMaxNB = 8;     // B (weight tile) stages
 constexpr uint32_t kSmemBudget = 188 * 1024;   // A + B stages
 constexpr uint32_t kStageOutBytes = kEpiWarps * 4096;  // epilogue transpose buffers: per warp [32 rows][64 cols] bf16
+constexpr int kBiasSmemFloats = 1024;                  // bias of every N tile of the launch, staged once (when it fits)
 
 constexpr int kMaxA = 6;  // A sources: 2 concat sources x 3 split-tier passes, or the 4 convT sub-lattices
 
@@ -113,7 +114,8 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
   uint8_t* sA = smem;
   uint8_t* sB = sA + kNA * a.a_stage_bytes;
   uint8_t* sOut = sB + (uint32_t)a.nb_stages * B_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + kStageOutBytes);
+  float* sBias = reinterpret_cast<float*>(sOut + kStageOutBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + kBiasSmemFloats);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kNA;
   uint64_t* b_full = a_empty + kNA;
@@ -149,6 +151,16 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < a.num_a; ++s) tma_prefetch_desc(&maps.a[s]);
     tma_prefetch_desc(&maps.b);
+  }
+  // Bias of all N tiles in shared memory (column nc of the GEMM -> channel nc - d * dst_c0 of its destination d; zero past
+  // cout_total).  The epilogue pre-loads it into the TMEM accumulators; fetching it from global memory there put an L2
+  // round trip on the critical path of every (M-block, pass) item (ncu: 15 % of the epilogue warps' time).
+  const bool bias_smem = a.bias != nullptr && a.n_ntiles * BN <= kBiasSmemFloats;
+  if (bias_smem) {
+    for (int i = threadIdx.x; i < a.n_ntiles * BN; i += kUmmaThreads) {
+      const int d = a.ndst > 1 ? min(i / a.dst_c0, a.ndst - 1) : 0;
+      sBias[i] = i < a.cout_total ? a.bias[i - d * a.dst_c0] : 0.f;
+    }
   }
   if (warp == 2) {
     if (CL == 2) tmem_alloc2<TMEM_COLS>(tmem_slot); else tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -330,19 +342,31 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     auto preload_item = [&](int n0, int buf, int mb, int c0) {
 #pragma unroll 1
       for (int col0 = c0; col0 < c0 + CP; col0 += 32) {
-        // several destinations (ConvTranspose quadrants) share one bias vector: column -> channel inside its destination
         const int nc = n0 + col0;
-        const int d = a.ndst > 1 ? min(nc / a.dst_c0, a.ndst - 1) : 0;
-        const float* bp = a.bias + (nc - d * a.dst_c0);
         uint32_t bv[32];
+        if (bias_smem) {  // warp-uniform broadcast reads
+          const uint32_t bs = smem_u32(sBias + nc);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (nc + 4 * j < a.cout_total) f = *reinterpret_cast<const float4*>(bp + 4 * j);
-          bv[4 * j] = __float_as_uint(f.x);
-          bv[4 * j + 1] = __float_as_uint(f.y);
-          bv[4 * j + 2] = __float_as_uint(f.z);
-          bv[4 * j + 3] = __float_as_uint(f.w);
+          for (int j = 0; j < 8; ++j) {
+            const uint4 f = ld_shared_v4(bs + 16 * j);
+            bv[4 * j] = f.x;
+            bv[4 * j + 1] = f.y;
+            bv[4 * j + 2] = f.z;
+            bv[4 * j + 3] = f.w;
+          }
+        } else {
+          // several destinations (ConvTranspose quadrants) share one bias vector: column -> channel inside its destination
+          const int d = a.ndst > 1 ? min(nc / a.dst_c0, a.ndst - 1) : 0;
+          const float* bp = a.bias + (nc - d * a.dst_c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (nc + 4 * j < a.cout_total) f = *reinterpret_cast<const float4*>(bp + 4 * j);
+            bv[4 * j] = __float_as_uint(f.x);
+            bv[4 * j + 1] = __float_as_uint(f.y);
+            bv[4 * j + 2] = __float_as_uint(f.z);
+            bv[4 * j + 3] = __float_as_uint(f.w);
+          }
         }
         tmem_st_32x32(tmem_base + buf * (MB * BN) + mb * BN + col0 + lane_base, bv);
       }
@@ -365,7 +389,7 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) {
-        if (CL == 2) mbar_arrive_cluster(&t_empty[b], 0); else mbar_arrive(&t_empty[b]);
+        if (CL == 2) mbar_arrive_remote(&t_empty[b], 0); else mbar_arrive(&t_empty[b]);
       }
     }
 
@@ -468,13 +492,12 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
               for (int i = 0; i < LPR; ++i) {
                 const int R = i * RPI + rsub;
                 if (offs[i] >= 0) {
-                  const uint4 c = ld_shared_v4(stg_s + (uint32_t)(R * LPR + (cch ^ (R & (LPR - 1)))) * 16);
-                  float f[8], m[8];
-                  unpack8(c, f);
-                  unpack8(mv[i], m);
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) f[j] = m[j] > 0.f ? f[j] : 0.f;
-                  *reinterpret_cast<uint4*>(dp + offs[i]) = pack8(f);
+                  uint4 c = ld_shared_v4(stg_s + (uint32_t)(R * LPR + (cch ^ (R & (LPR - 1)))) * 16);
+                  c.x &= bf16x2_gt0_mask(mv[i].x);  // on the packed pairs: 2 instructions per pair
+                  c.y &= bf16x2_gt0_mask(mv[i].y);
+                  c.z &= bf16x2_gt0_mask(mv[i].z);
+                  c.w &= bf16x2_gt0_mask(mv[i].w);
+                  *reinterpret_cast<uint4*>(dp + offs[i]) = c;
                 }
               }
             } else {
@@ -494,7 +517,7 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) {
-        if (CL == 2) mbar_arrive_cluster(&t_empty[buf], 0); else mbar_arrive(&t_empty[buf]);
+        if (CL == 2) mbar_arrive_remote(&t_empty[buf], 0); else mbar_arrive(&t_empty[buf]);
       }
     }
   }
@@ -527,6 +550,19 @@ static bool aligned_view(const b200_view& v) {
   const int64_t span = (int64_t)(v.h - 1) * v.stride_h + (int64_t)(v.w - 1) * v.stride_w + v.c;
   return v.c % 8 == 0 && reinterpret_cast<uintptr_t>(v.ptr) % 16 == 0 && reinterpret_cast<uintptr_t>(v.lo) % 16 == 0 &&
          v.stride_w % 8 == 0 && v.stride_h % 8 == 0 && (v.n == 1 || v.stride_n % 8 == 0) && span < (int64_t(1) << 31);
+}
+
+// 1x1 / transposed convolutions have no halo, so nothing separates the images of a batch: when every view involved is
+// "row-contiguous across images" (stride_n == h * stride_h) the batch is folded into the row dimension and pixel tiles
+// run across image boundaries.  With 28 x 28 images and 256-position tiles that is 100 tiles instead of 128 (the last
+// tile of each image was 1 row of 9), and the kernel itself does not change.
+static bool foldable(const b200_view& v) { return v.n == 1 || v.stride_n == (int64_t)v.h * v.stride_h; }
+static b200_view fold_batch(const b200_view& v) {
+  b200_view f = v;
+  f.h = v.n * v.h;
+  f.n = 1;
+  f.stride_n = (int64_t)f.h * v.stride_h;
+  return f;
 }
 
 static b200_view lo_plane(const b200_view& v) {  // the low-order plane of a split-tier view, as a plain view
@@ -610,7 +646,8 @@ static bool make_plan(int Ho, int Wo, int n_img, int halo, int cout_total, int n
   if (nb > kMaxNB) nb = kMaxNB;
   if (nb < 2) return false;
   pl->nb_stages = nb;
-  pl->smem_bytes = kNA * pl->a_stage_bytes + nb * b_stage + kStageOutBytes + 1024 /*align*/ + 512 /*barriers*/;
+  pl->smem_bytes = kNA * pl->a_stage_bytes + nb * b_stage + kStageOutBytes + kBiasSmemFloats * 4 + 1024 /*align*/ +
+                   512 /*barriers*/;
   return true;
 }
 
@@ -635,7 +672,7 @@ static int launch_inst(const TileMaps& maps, const UmmaArgs& a, const Plan& pl, 
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(kSmemBudget + kStageOutBytes + 2048));
+                                         (int)(kSmemBudget + kStageOutBytes + kBiasSmemFloats * 4 + 2048));
     if (e != cudaSuccess) return fail((int)e, "umma_conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_done = true;
   }
@@ -701,6 +738,44 @@ static int fwd_k_work(const b200_conv_fwd_params* p) {
   return chunks * (p->dst.lo ? 3 : 1) * p->taps;
 }
 
+static bool folded_span_ok(const b200_view& v) {  // 32-bit element offsets inside the (folded) image
+  return (int64_t)(v.n * (int64_t)v.h - 1) * v.stride_h + (int64_t)(v.w - 1) * v.stride_w + v.c < (int64_t(1) << 31);
+}
+
+// 1x1 convolution: fold the batch into the rows when every view allows it (see fold_batch)
+static const b200_conv_fwd_params* fold_conv_fwd(const b200_conv_fwd_params* p, b200_conv_fwd_params* tmp) {
+  if (p->taps != 1 || p->dst.n == 1 || !foldable(p->dst) || !folded_span_ok(p->dst)) return p;
+  for (int i = 0; i < p->num_src; ++i)
+    if (!foldable(p->src[i]) || !folded_span_ok(p->src[i])) return p;
+  *tmp = *p;
+  tmp->dst = fold_batch(p->dst);
+  for (int i = 0; i < p->num_src; ++i) tmp->src[i] = fold_batch(p->src[i]);
+  return tmp;
+}
+static const b200_conv_dgrad_params* fold_conv_dgrad(const b200_conv_dgrad_params* p, b200_conv_dgrad_params* tmp) {
+  if (p->taps != 1 || p->dz.n == 1 || !foldable(p->dz) || !folded_span_ok(p->dz)) return p;
+  for (int i = 0; i < p->num_dst; ++i)
+    if (!foldable(p->dst[i]) || !folded_span_ok(p->dst[i])) return p;  // masks are laid out like their destinations
+  *tmp = *p;
+  tmp->dz = fold_batch(p->dz);
+  for (int i = 0; i < p->num_dst; ++i) tmp->dst[i] = fold_batch(p->dst[i]);
+  return tmp;
+}
+static const b200_convt_fwd_params* fold_convt_fwd(const b200_convt_fwd_params* p, b200_convt_fwd_params* tmp) {
+  if (p->x.n == 1 || !foldable(p->x) || !foldable(p->y) || !folded_span_ok(p->x) || !folded_span_ok(p->y)) return p;
+  *tmp = *p;
+  tmp->x = fold_batch(p->x);
+  tmp->y = fold_batch(p->y);  // rows 2i + a of the folded y: image n starts at row 2 * (n * h) = n * (2h)
+  return tmp;
+}
+static const b200_convt_dgrad_params* fold_convt_dgrad(const b200_convt_dgrad_params* p, b200_convt_dgrad_params* tmp) {
+  if (p->dx.n == 1 || !foldable(p->dx) || !foldable(p->dy) || !folded_span_ok(p->dx) || !folded_span_ok(p->dy)) return p;
+  *tmp = *p;
+  tmp->dx = fold_batch(p->dx);
+  tmp->dy = fold_batch(p->dy);
+  return tmp;
+}
+
 bool umma_conv_fwd_ok(const b200_conv_fwd_params* p) {
   if (!device_is_sm100()) return false;
   for (int i = 0; i < p->num_src; ++i)
@@ -713,6 +788,8 @@ bool umma_conv_fwd_ok(const b200_conv_fwd_params* p) {
 
 int umma_conv_fwd(const b200_conv_fwd_params* p, cudaStream_t st) {
   if (!p->w_packed) return fail(-1, "conv_fwd (tcgen05): w_packed is required");
+  b200_conv_fwd_params folded;
+  p = fold_conv_fwd(p, &folded);
   const int halo = p->taps == 9 ? 2 : 0;
   Plan pl;
   if (!make_plan(p->dst.h, p->dst.w, p->dst.n, halo, p->dst.c, 1, p->dst.c, fwd_k_work(p), &pl))
@@ -776,6 +853,8 @@ bool umma_conv_dgrad_ok(const b200_conv_dgrad_params* p) {
 
 int umma_conv_dgrad(const b200_conv_dgrad_params* p, cudaStream_t st) {
   if (!p->w_packed) return fail(-1, "conv_dgrad (tcgen05): w_packed is required");
+  b200_conv_dgrad_params folded;
+  p = fold_conv_dgrad(p, &folded);
   const int halo = p->taps == 9 ? 2 : 0;
   const int cin = dgrad_cin(p);
   Plan pl;
@@ -830,6 +909,8 @@ bool umma_convt_fwd_ok(const b200_convt_fwd_params* p) {
 
 int umma_convt_fwd(const b200_convt_fwd_params* p, cudaStream_t st) {
   if (!p->w_packed) return fail(-1, "convt_fwd (tcgen05): w_packed is required");
+  b200_convt_fwd_params folded;
+  p = fold_convt_fwd(p, &folded);
   Plan pl;
   if (!make_plan(p->x.h, p->x.w, p->x.n, 0, 4 * p->y.c, 4, p->y.c, (p->x.c + 63) / 64 * (p->y.lo ? 3 : 1), &pl))
     return fail(-1, "convt_fwd: no plan");
@@ -876,6 +957,8 @@ bool umma_convt_dgrad_ok(const b200_convt_dgrad_params* p) {
 
 int umma_convt_dgrad(const b200_convt_dgrad_params* p, cudaStream_t st) {
   if (!p->w_packed) return fail(-1, "convt_dgrad (tcgen05): w_packed is required");
+  b200_convt_dgrad_params folded;
+  p = fold_convt_dgrad(p, &folded);
   Plan pl;
   if (!make_plan(p->dx.h, p->dx.w, p->dx.n, 0, p->dx.c, 1, p->dx.c, 4 * ((p->dy.c + 63) / 64), &pl))
     return fail(-1, "convt_dgrad: no plan");

@@ -276,6 +276,319 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(HeadArgs a) {
   }
 }
 
+
+// ------------------------------------------------------------------ fast path (dense tensors, 8..64 channels)
+// The first version of this kernel (head_kernel above, kept for strided views / wide heads) has ONE 16-byte load in
+// flight per thread and iteration and reached 1.5-2.0 TB/s (ncu: long-scoreboard stalls, l1tex 52 %).  Here every thread
+// owns U pixels per iteration: all U loads (and the labels) are issued before any arithmetic, LPP = C/8 lanes cooperate
+// on a pixel (a warp instruction reads 512 contiguous bytes), the classifier weights of the thread's 8 channels live in
+// registers, and the loop is grid-strided over contiguous chunks of (256/LPP)*U pixels.
+constexpr int kHeadDenseU = 4;   // pixels per thread and stage
+constexpr int kHeadStages = 4;   // cp.async ring depth
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+inline size_t head_ring_bytes(int lpp, bool split) {
+  return (size_t)kHeadStages * kHeadDenseU * (kHeadThreads * 16 * (split ? 2 : 1) + (kHeadThreads / lpp) * 8);
+}
+template <int KMAX, int LPP, int MODE, int U, bool SPLIT>
+__global__ void __launch_bounds__(kHeadThreads, 2) head_dense_kernel(HeadArgs a, long long npix) {
+  constexpr int PPB = kHeadThreads / LPP;   // pixels per block and sub-iteration
+  constexpr bool BWD = MODE == HEAD_BWD || MODE == HEAD_CE_BWD;
+  constexpr bool CE = MODE == HEAD_CE_FWD || MODE == HEAD_CE_BWD;
+  __shared__ float red[kHeadThreads / 32][KMAX * LPP * 8 + KMAX + 2];
+  const int K = a.k, c = LPP * 8;
+  const int lip = threadIdx.x % LPP;        // lane in pixel: owns channels lip*8 .. +7
+  const int slot = threadIdx.x / LPP;
+  float w[KMAX][8], bias[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    bias[k] = (k < K && a.b) ? a.b[k] : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[k][j] = k < K ? a.w[k * c + lip * 8 + j] : 0.f;
+  }
+  float dw_acc[BWD ? KMAX : 1][8], db_acc[KMAX];
+  float loss_acc = 0.f, cnt_acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    db_acc[k] = 0.f;
+    if (BWD) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dw_acc[k][j] = 0.f;
+    }
+  }
+  float gs = 1.f;
+  if (MODE == HEAD_CE_BWD) gs = (a.gscale ? a.gscale[0] : 1.f) * a.ce_state[1];
+  const long long hw = (long long)a.x.h * a.x.w;
+  const bf16* __restrict__ xp = a.x.p;
+  const bf16* __restrict__ xlo = SPLIT ? a.x.lo : nullptr;
+
+  // Multi-stage cp.async ring (thread-private 16-byte slots, so no block barrier): S stages of U vectors per thread
+  // are in flight — S*U*16 B = 256 B per thread, 128 KB per SM at 2 blocks — without holding them in registers.  With one
+  // round of register loads per iteration (512 threads x 64 B per SM and memory round trip) the kernel was latency-bound
+  // at 1.6 TB/s; prefetching the next round into registers cost occupancy and was slower still.
+  extern __shared__ __align__(16) uint8_t ring_raw[];
+  uint4* xb = reinterpret_cast<uint4*>(ring_raw);                                        // [S][U][256]
+  uint4* xlb = xb + (SPLIT ? kHeadStages * U * kHeadThreads : 0);                        // [S][U][256] (split tier)
+  long long* lb = reinterpret_cast<long long*>(xlb + kHeadStages * U * kHeadThreads);    // [S][U][PPB]
+  const long long stride = (long long)gridDim.x * (PPB * U);
+  const long long base0 = (long long)blockIdx.x * (PPB * U);
+  auto issue = [&](int stage, long long b) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long p = b + u * PPB + slot;
+      if (p < npix) {
+        cp_async_16(&xb[(stage * U + u) * kHeadThreads + threadIdx.x], xp + p * c + lip * 8);
+        if (SPLIT) cp_async_16(&xlb[(stage * U + u) * kHeadThreads + threadIdx.x], xlo + p * c + lip * 8);
+        if (CE && lip == 0) cp_async_8(&lb[(stage * U + u) * PPB + slot], a.labels + p);
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int st = 0; st < kHeadStages - 1; ++st) issue(st, base0 + st * stride);
+  int stage = 0;
+  for (long long base = base0; base < npix; base += stride) {
+    __syncwarp();  // every lane has read the label slots of the stage that is refilled now
+    issue(stage == 0 ? kHeadStages - 1 : stage - 1, base + (kHeadStages - 1) * stride);
+    cp_async_wait<kHeadStages - 1>();
+    __syncwarp();  // labels are written by lane lip == 0 of each pixel
+    bf16x8 xv[U], xl[SPLIT ? U : 1];
+    int lab[U];
+    bool live[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long p = base + u * PPB + slot;
+      live[u] = p < npix;
+      xv[u] = make_uint4(0, 0, 0, 0);
+      if (SPLIT) xl[u] = make_uint4(0, 0, 0, 0);
+      lab[u] = -1;  // class, or -1 = ignore_index, or -2 = out of range (poisons the loss)
+      if (live[u]) {
+        xv[u] = xb[(stage * U + u) * kHeadThreads + threadIdx.x];
+        if (SPLIT) xl[u] = xlb[(stage * U + u) * kHeadThreads + threadIdx.x];
+        if (CE) {
+          const long long l64 = lb[(stage * U + u) * PPB + slot];
+          lab[u] = l64 == kIgnoreIndex ? -1 : ((l64 < 0 || l64 >= K) ? -2 : (int)l64);
+        }
+      }
+    }
+    stage = stage + 1 == kHeadStages ? 0 : stage + 1;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long p = base + u * PPB + slot;
+      float x8[8];
+      unpack8(xv[u], x8);
+      if (SPLIT) {  // split tier (forward modes): x = hi + lo
+        float t[8];
+        unpack8(xl[u], t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x8[j] += t[j];
+      }
+      float z[KMAX];
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += x8[j] * w[k][j];
+#pragma unroll
+        for (int o = 1; o < LPP; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        z[k] = s + bias[k];
+      }
+      float zr[KMAX];
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) zr[k] = a.relu ? fmaxf(z[k], 0.f) : z[k];
+      const long long n = p / hw, r = p - n * hw;
+      if (!BWD && a.logits && live[u]) {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+          if (k < K && k % LPP == lip) a.logits[(n * K + k) * hw + r] = zr[k];
+      }
+      if (MODE == HEAD_FWD) continue;
+      bool valid = live[u];
+      float lse = 0.f;
+      if (CE) {
+        valid = live[u] && lab[u] != -1;
+        float m = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+          if (k < K) m = fmaxf(m, zr[k]);
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+          if (k < K) sum += __expf(zr[k] - m);
+        lse = m + __logf(sum);
+      }
+      if (MODE == HEAD_CE_FWD) {
+        if (valid && lip == 0) {
+          float zy = 0.f;
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k)
+            if (k == lab[u]) zy = zr[k];
+          if (lab[u] == -2) zy = __int_as_float(0x7fc00000);  // out-of-range label: poison the loss
+          loss_acc += lse - zy;
+          cnt_acc += 1.f;
+        }
+        continue;
+      }
+      if (BWD) {
+        float dz[KMAX];
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          float g = 0.f;
+          if (k < K && valid) {
+            if (MODE == HEAD_CE_BWD)
+              g = gs * (__expf(zr[k] - lse) - (k == lab[u] ? 1.f : 0.f));
+            else
+              g = a.dlogits[(n * K + k) * hw + r];
+            if (a.relu && !(z[k] > 0.f)) g = 0.f;
+          }
+          dz[k] = g;
+        }
+        float rr[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rr[j] = 0.f;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            rr[j] += dz[k] * w[k][j];
+            dw_acc[k][j] += dz[k] * x8[j];
+          }
+          if (lip == 0) db_acc[k] += dz[k];
+        }
+        if (a.dx.p && live[u]) {
+          if (a.mask) {  // fast path: the mask IS x (no BatchNorm): ReLU backward of the last convolution
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rr[j] = x8[j] > 0.f ? rr[j] : 0.f;
+          }
+          *reinterpret_cast<bf16x8*>(a.dx.p + p * c + lip * 8) = pack8(rr);
+        }
+      }
+    }
+  }
+  if (MODE == HEAD_FWD) return;
+
+  // ---- deterministic block reduction: lanes with the same `lip` by shuffle, warps through shared memory
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kRowD = KMAX * LPP * 8;
+  if (MODE == HEAD_CE_FWD) {
+#pragma unroll
+    for (int o = LPP; o < 32; o <<= 1) {
+      loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
+      cnt_acc += __shfl_xor_sync(0xffffffffu, cnt_acc, o);
+    }
+    if (lane == 0) {
+      red[warp][0] = loss_acc;
+      red[warp][1] = cnt_acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float l = 0.f, cn = 0.f;
+      for (int wdx = 0; wdx < kHeadThreads / 32; ++wdx) {
+        l += red[wdx][0];
+        cn += red[wdx][1];
+      }
+      a.ws[blockIdx.x * 2 + 0] = l;
+      a.ws[blockIdx.x * 2 + 1] = cn;
+    }
+    return;
+  }
+  if (BWD) {
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = dw_acc[k][j];
+#pragma unroll
+        for (int o = LPP; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane < LPP) red[warp][(k * LPP + lane) * 8 + j] = v;
+      }
+      float d = db_acc[k];
+#pragma unroll
+      for (int o = LPP; o < 32; o <<= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      if (lane == 0) red[warp][kRowD + k] = d;
+    }
+    __syncthreads();
+    float* out = a.ws + (long long)blockIdx.x * (K * c + K);   // partial layout of head_kernel: [K*c + K]
+    for (int q = threadIdx.x; q < kRowD; q += blockDim.x) {
+      const int k = q / (LPP * 8), ch = q - k * (LPP * 8);
+      if (k < K) {
+        float sacc = 0.f;
+        for (int wdx = 0; wdx < kHeadThreads / 32; ++wdx) sacc += red[wdx][q];
+        out[k * c + ch] = sacc;
+      }
+    }
+    if (threadIdx.x < K) {
+      float sacc = 0.f;
+      for (int wdx = 0; wdx < kHeadThreads / 32; ++wdx) sacc += red[wdx][kRowD + threadIdx.x];
+      out[K * c + threadIdx.x] = sacc;
+    }
+  }
+}
+
+inline bool dense_nhwc(const DView& v) {
+  return v.sw == v.c && v.sh == (long long)v.w * v.sw && v.sn == (long long)v.h * v.sh;
+}
+
+template <int MODE, int KMAX, int LPP>
+void launch_head_dense_inst(const HeadArgs& a, int blocks, long long npix, cudaStream_t st) {
+  constexpr bool FWD = MODE == HEAD_FWD || MODE == HEAD_CE_FWD;  // only the forward modes read the lo plane
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(head_dense_kernel<KMAX, LPP, MODE, kHeadDenseU, FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)head_ring_bytes(LPP, true));
+    cudaFuncSetAttribute(head_dense_kernel<KMAX, LPP, MODE, kHeadDenseU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)head_ring_bytes(LPP, false));
+    attr_done = true;
+  }
+  if (FWD && a.x.lo)
+    head_dense_kernel<KMAX, LPP, MODE, kHeadDenseU, FWD><<<blocks, kHeadThreads, head_ring_bytes(LPP, true), st>>>(a, npix);
+  else
+    head_dense_kernel<KMAX, LPP, MODE, kHeadDenseU, false><<<blocks, kHeadThreads, head_ring_bytes(LPP, false), st>>>(a, npix);
+}
+
+// returns true if the fast kernel took the launch
+template <int MODE>
+bool launch_head_dense(const HeadArgs& a, int* blocks_io, cudaStream_t st) {
+  constexpr bool BWD = MODE == HEAD_BWD || MODE == HEAD_CE_BWD;
+  const int c = a.x.c, K = a.k;
+  if (!(c == 8 || c == 16 || c == 32 || c == 64) || !dense_nhwc(a.x)) return false;
+  if (K > 4) return false;  // 8 classes x 8 channels of weights (+ as many dW accumulators) in registers: measured slower
+  if (reinterpret_cast<uintptr_t>(a.x.p) % 16 || reinterpret_cast<uintptr_t>(a.x.lo) % 16) return false;
+  if (BWD) {
+    if (a.x.lo) return false;  // backward entry points read the hi plane only, and the general kernel handles it
+    if (a.dx.p && (!dense_nhwc(a.dx) || reinterpret_cast<uintptr_t>(a.dx.p) % 16)) return false;
+    if (a.mask && a.mask != a.x.p) return false;  // a separate mask tensor: general kernel
+  }
+  const long long npix = (long long)a.x.n * a.x.h * a.x.w;
+  const int lpp = c / 8;
+  const long long per_block = (kHeadThreads / lpp) * kHeadDenseU;
+  long long blocks = (npix + per_block - 1) / per_block;
+  if (blocks > kHeadMaxBlocks) blocks = kHeadMaxBlocks;
+  if (blocks < 1) blocks = 1;
+  *blocks_io = (int)blocks;
+  const int kmax = K <= 2 ? 2 : 4;
+#define B200_HD(KM, L) launch_head_dense_inst<MODE, KM, L>(a, (int)blocks, npix, st)
+#define B200_HD_K(L)            \
+  do {                          \
+    if (kmax == 2) B200_HD(2, L);      \
+    else B200_HD(4, L);                \
+  } while (0)
+  if (lpp == 8) B200_HD_K(8);
+  else if (lpp == 4) B200_HD_K(4);
+  else if (lpp == 2) B200_HD_K(2);
+  else B200_HD_K(1);
+#undef B200_HD_K
+#undef B200_HD
+  return true;
+}
+
 __global__ void head_ce_finalize_kernel(const float* __restrict__ ws, int blocks, float* __restrict__ loss,
                                         float* __restrict__ ce_state) {
   if (threadIdx.x >= 32 || blockIdx.x != 0) return;
@@ -301,7 +614,9 @@ __global__ void head_bwd_finalize_kernel(const float* __restrict__ ws, int block
 }
 
 template <int MODE>
-int launch_head(const HeadArgs& a, int blocks, cudaStream_t st) {
+int launch_head(const HeadArgs& a, int* blocks_io, cudaStream_t st) {
+  if (launch_head_dense<MODE>(a, blocks_io, st)) return check_launch("head (dense)");
+  const int blocks = *blocks_io;
   const int c = a.x.c, K = a.k;
   const bool v8 = c % 8 == 0 && reinterpret_cast<uintptr_t>(a.x.p) % 16 == 0 && a.x.sw % 8 == 0 && a.x.sh % 8 == 0 &&
                   a.x.sn % 8 == 0 &&
@@ -357,7 +672,8 @@ int b200unet_head_fwd(const b200_view* x, const float* w, const float* b, int n_
   a.k = n_classes;
   a.relu = relu;
   a.logits = logits_nchw;
-  return launch_head<HEAD_FWD>(a, head_blocks(view_pixels(*x)), as_stream(stream));
+  int blocks = head_blocks(view_pixels(*x));
+  return launch_head<HEAD_FWD>(a, &blocks, as_stream(stream));
 }
 
 int b200unet_head_bwd(const b200_view* x, const float* w, const float* b, int n_classes, int relu,
@@ -377,8 +693,8 @@ int b200unet_head_bwd(const b200_view* x, const float* w, const float* b, int n_
   if (dx) a.dx = dview(*dx);
   a.mask = (const bf16*)mask;
   a.ws = (float*)workspace;
-  const int blocks = head_blocks(view_pixels(*x));
-  int r = launch_head<HEAD_BWD>(a, blocks, as_stream(stream));
+  int blocks = head_blocks(view_pixels(*x));
+  int r = launch_head<HEAD_BWD>(a, &blocks, as_stream(stream));
   if (r) return r;
   const int kc = n_classes * x->c;
   head_bwd_finalize_kernel<<<finalize_grid(kc + n_classes), kFinalizeThreads, 0, as_stream(stream)>>>((const float*)workspace, blocks,
@@ -401,8 +717,8 @@ int b200unet_head_ce_fwd(const b200_view* x, const float* w, const float* b, int
   a.logits = logits_nchw;
   a.labels = (const long long*)labels;
   a.ws = (float*)workspace;
-  const int blocks = head_blocks(view_pixels(*x));
-  int r = launch_head<HEAD_CE_FWD>(a, blocks, as_stream(stream));
+  int blocks = head_blocks(view_pixels(*x));
+  int r = launch_head<HEAD_CE_FWD>(a, &blocks, as_stream(stream));
   if (r) return r;
   head_ce_finalize_kernel<<<1, 32, 0, as_stream(stream)>>>((const float*)workspace, blocks, loss, ce_state);
   return check_launch("head_ce finalize");
@@ -427,8 +743,8 @@ int b200unet_head_ce_bwd(const b200_view* x, const float* w, const float* b, int
   if (dx) a.dx = dview(*dx);
   a.mask = (const bf16*)mask;
   a.ws = (float*)workspace;
-  const int blocks = head_blocks(view_pixels(*x));
-  int r = launch_head<HEAD_CE_BWD>(a, blocks, as_stream(stream));
+  int blocks = head_blocks(view_pixels(*x));
+  int r = launch_head<HEAD_CE_BWD>(a, &blocks, as_stream(stream));
   if (r) return r;
   const int kc = n_classes * x->c;
   head_bwd_finalize_kernel<<<finalize_grid(kc + n_classes), kFinalizeThreads, 0, as_stream(stream)>>>((const float*)workspace, blocks,

@@ -148,6 +148,37 @@ __global__ void im2col3x3_kernel(DView src, DView dst, int pad) {
   }
 }
 
+// ------------------------------------------------------------------ uint8 HWC images -> the first convolution's operand
+// Input pipeline at the boundary.  The reference divides the uint8 image by 255 on the host
+// (dataloader.py:258-264), transposes it to CHW and uploads it as fp32 per sample (dataloader.py:553-579): 4 bytes per
+// value over PCIe, then the module converts fp32 NCHW -> bf16 NHWC.  Here the batch travels as uint8 NHWC (1 byte per
+// value, the layout image decoders produce) and ONE kernel writes dst[n,y,x,c] = src * scale[c] + shift[c] in the NHWC
+// bf16 layout (hi + lo planes in the split tier) that down_path.0 reads; channels >= src_c of dst stay zero.
+// scale = 1/255, shift = 0 reproduces the reference: the division is IEEE-rounded like fp32(u8 / 255.0).
+__global__ void u8_nhwc_to_bf16_kernel(const uint8_t* __restrict__ src, int src_c, DView dst, const float* __restrict__ scale,
+                                       const float* __restrict__ shift, int divide_255) {
+  const long long total = (long long)dst.n * dst.h * dst.w;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+    const int ix = (int)(p % dst.w);
+    const long long t = p / dst.w;
+    const int iy = (int)(t % dst.h), n = (int)(t / dst.h);
+    const long long o = dst.off(n, iy, ix);
+    const uint8_t* s = src + p * src_c;
+    for (int c = 0; c < dst.c; ++c) {
+      float v = 0.f;
+      if (c < src_c) {
+        v = (float)s[c];
+        v = divide_255 ? __fdiv_rn(v, 255.f) : v;
+        if (scale) v *= scale[c];
+        if (shift) v += shift[c];
+      }
+      const bf16 h = f2bf(v);
+      dst.p[o + c] = h;
+      if (dst.lo) dst.lo[o + c] = f2bf(split_lo(v, bf2f(h)));
+    }
+  }
+}
+
 // ------------------------------------------------------------------ y = mask > 0 ? x : 0
 __global__ void relu_mask_kernel(DView x, DView m, DView y) {
   const long long total = (long long)x.n * x.h * x.w * x.c;
@@ -202,6 +233,14 @@ int b200unet_nhwc_bf16_to_nchw_f32(const b200_view* src, float* dst, void* strea
   dim3 grid((unsigned)((total + 31) / 32), (unsigned)((src->c + 31) / 32));
   nhwc_to_nchw_kernel<<<grid, dim3(32, 32), 0, as_stream(stream)>>>(dview(*src), dst);
   return check_launch("nhwc_to_nchw");
+}
+
+int b200unet_u8_nhwc_to_bf16(const uint8_t* src, int src_c, const b200_view* dst, const float* scale, const float* shift,
+                             int divide_255, void* stream) {
+  B200_REQUIRE(src && view_ok(dst) && src_c >= 1 && src_c <= dst->c, "u8_nhwc_to_bf16: bad arguments");
+  u8_nhwc_to_bf16_kernel<<<grid_for(view_pixels(*dst), 256), 256, 0, as_stream(stream)>>>(src, src_c, dview(*dst), scale, shift,
+                                                                                      divide_255);
+  return check_launch("u8_nhwc_to_bf16");
 }
 
 int b200unet_im2col3x3(const b200_view* src, const b200_view* dst, int pad, void* stream) {

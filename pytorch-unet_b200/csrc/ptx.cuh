@@ -195,6 +195,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
   return d;
 }
 
+// per-half "a > 0" of a packed bf16 pair as a bit mask (0xffff / 0x0000 per half); NaN -> 0
+__device__ __forceinline__ uint32_t bf16x2_gt0_mask(uint32_t a) {
+  const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&a);
+  return __hgt2_mask(v, __floats2bfloat162_rn(0.f, 0.f));
+}
+
 // ------------------------------------------------------------------ thread-block clusters (CTA pairs sharing loads)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -278,7 +284,18 @@ __device__ __forceinline__ void tma_load_4d_2cta(const CUtensorMap* m, uint64_t*
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
-// arrive on the mbarrier at the same offset in CTA `cta` of the cluster
+// arrive on the mbarrier at the same offset in CTA `cta` of the cluster, default semantics (.release at CTA scope): what
+// a consumer uses to hand a TMEM buffer back — the tcgen05 accesses are ordered by tcgen05.fence::before_thread_sync, no
+// ordinary memory has to become visible to the peer.  (The .release.cluster form below compiles to MEMBAR.ALL.GPU +
+// ERRBAR, which waits for every outstanding global store of the warp: measured 18 % of the epilogue warps' time.)
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
