@@ -15,6 +15,7 @@
  *   head_ce_fwd / head_ce_bwd            head fused with F.cross_entropy                   README.md:58
  *   nchw_f32_to_nhwc_bf16, nhwc_bf16_to_nchw_f32, pack_*   boundary layout / precision transforms
  *   adam_plan / adam_upload / adam_step               torch.optim.Adam(model.parameters()).step()       README.md:49, run.py:71
+ *   cvo_*                                the CVO kernel-Gramian loss that consumes the features    geometry.py:13-136
  *
  * Conventions
  *   - Activations and activation gradients are bf16, NHWC ("pixels x channels"), described by b200_view.  A
@@ -284,6 +285,43 @@ int b200unet_adam_plan(b200_adam_job* jobs_host, int num_jobs);
 int b200unet_adam_upload(b200_adam_job* jobs_dev, const b200_adam_job* jobs_host, int num_jobs, void* stream);
 int b200unet_adam_step(const b200_adam_job* jobs_dev, int num_jobs, int total_blocks, float lr, float beta1,
                        float beta2, float eps, float weight_decay, const float* step_dev, void* stream);
+
+/* ---- CVO kernel-Gramian loss: the step after the U-Net in the reference's own pipeline.
+ * Replaces the three CUDA extensions geometry.py:4 imports (sub_norm_cuda_half_paral, cross_prod_cuda,
+ * cross_subtract_cuda — source absent from the reference tree) and the PyTorch chain around them:
+ *   cvo_sub_norm_fwd / bwd    SubNormFunction.forward / backward                     geometry.py:13-25
+ *   cvo_kern_mat_fwd / bwd    kern_mat: exp(-d / (2 s^2)) zeroed below 8.315e-3      geometry.py:47-136
+ *   cvo_cross_fwd             cross_prod / cross_subtract                            geometry.py:27-45
+ *   cvo_inner_prod_fwd / bwd  calc_gramian + calc_inner_prod (+ calc_w_v) fused: no N1 x N2 matrix is ever stored
+ *                                                                     network_modules.py:995-1015, 1052-1149
+ * Point sets are fp32, channel-planar x[b][c][n] (the reference's B*C*N tensors, contiguous).  Matrices are [b][n1][n2].
+ * `workspace`: b200unet_cvo_workspace_bytes(b, n1, n2, total channels) bytes of device memory (caller-owned).       */
+typedef struct {
+  const float* x1; /* [b][c][n1] */
+  const float* x2; /* [b][c][n2] */
+  int32_t c;
+  float dist_coef; /* RBF scale s of this domain; <= 0: plain inner product sum_c x1 x2 (`not kernalize`), at most one */
+} b200_cvo_item;
+size_t b200unet_cvo_workspace_bytes(int b, int n1, int n2, int total_c);
+int b200unet_cvo_sub_norm_fwd(const float* x1, const float* x2, int b, int c, int n1, int n2, float* out, void* stream);
+int b200unet_cvo_sub_norm_bwd(const float* dy, const float* x1, const float* x2, int b, int c, int n1, int n2,
+                              float* workspace, float* dx1, float* dx2, void* stream);
+int b200unet_cvo_kern_mat_fwd(const float* x1, const float* x2, int b, int c, int n1, int n2, float dist_coef, float* out,
+                              void* stream);
+int b200unet_cvo_kern_mat_bwd(const float* dy, const float* x1, const float* x2, int b, int c, int n1, int n2,
+                              float dist_coef, float* workspace, float* dx1, float* dx2, void* stream);
+/* out[b][n1][n2][3] = x1_i x x2_j (subtract == 0) or x1_i - x2_j (subtract != 0); 3-channel point sets */
+int b200unet_cvo_cross_fwd(const float* x1, const float* x2, int b, int n1, int n2, int subtract, float* out, void* stream);
+/* out[b] = sum_ij w1_i w2_j prod_k K_k[i][j] over 1..4 domains (at most 16 channels in total); w1 / w2: [b][n] or NULL.
+ * wv (NULL, or [b][6]) receives sum_ij P_ij (x1_i x x2_j) and sum_ij P_ij (x1_i - x2_j) of domain `geo_item` (3 channels),
+ * un-normalised (calc_w_v divides by the 6-vector norm on the host side).                                             */
+int b200unet_cvo_inner_prod_fwd(const b200_cvo_item* items, int num_items, const float* w1, const float* w2, int b, int n1,
+                                int n2, int geo_item, float* workspace, float* out, float* wv, void* stream);
+/* grad_out: [b] device floats (NULL = ones).  dx1 / dx2: host arrays of num_items device pointers (entries or the array may
+ * be NULL) receiving the gradients of items[k].x1 / .x2; dw1 / dw2: gradients of w1 / w2 or NULL.                      */
+int b200unet_cvo_inner_prod_bwd(const b200_cvo_item* items, int num_items, const float* w1, const float* w2, int b, int n1,
+                                int n2, const float* grad_out, float* workspace, float* const* dx1, float* const* dx2,
+                                float* dw1, float* dw2, void* stream);
 
 #ifdef __cplusplus
 }

@@ -8,12 +8,12 @@
 The compute path is libb200unet.so (C ABI in include/b200unet.h); importing this package does not need a GPU,
 running it does.
 """
-from . import ops  # noqa: F401
+from . import cvo, ops  # noqa: F401
 from ._lib import IMPL_AUTO, IMPL_DIRECT, IMPL_UMMA, LIB_PATH, load as load_library  # noqa: F401
 from .graph import GraphedTrainStep  # noqa: F401
 from .input import ImageStager, PackedImages, pack_images  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 from .unet import UNet, UNetConvBlock, UNetUpBlock, UNetUpBlockDeep  # noqa: F401
 
-__all__ = ["UNet", "FusedAdam", "GraphedTrainStep", "ImageStager", "PackedImages", "pack_images", "UNetConvBlock", "UNetUpBlock", "UNetUpBlockDeep", "ops", "load_library", "IMPL_AUTO",
+__all__ = ["UNet", "FusedAdam", "GraphedTrainStep", "ImageStager", "PackedImages", "pack_images", "UNetConvBlock", "UNetUpBlock", "UNetUpBlockDeep", "ops", "cvo", "load_library", "IMPL_AUTO",
            "IMPL_DIRECT", "IMPL_UMMA"]

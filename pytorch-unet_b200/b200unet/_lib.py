@@ -54,6 +54,12 @@ class ConvTWgradParams(C.Structure):
     _fields_ = [("x", View), ("dy", View), ("dw_f32", C.c_void_p), ("db_f32", C.c_void_p), ("impl", C.c_int32)]
 
 
+class CvoItem(C.Structure):
+    """b200_cvo_item"""
+
+    _fields_ = [("x1", C.c_void_p), ("x2", C.c_void_p), ("c", C.c_int32), ("dist_coef", C.c_float)]
+
+
 class AdamJob(C.Structure):
     """b200_adam_job"""
 
@@ -116,6 +122,15 @@ SIGNATURES = {
     "b200unet_adam_plan": (_I, [C.POINTER(AdamJob), _I]),
     "b200unet_adam_upload": (_I, [_P, C.POINTER(AdamJob), _I, _P]),
     "b200unet_adam_step": (_I, [_P, _I, _I, _F, _F, _F, _F, _F, _P, _P]),
+    "b200unet_cvo_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
+    "b200unet_cvo_sub_norm_fwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
+    "b200unet_cvo_sub_norm_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "b200unet_cvo_kern_mat_fwd": (_I, [_P, _P, _I, _I, _I, _I, _F, _P, _P]),
+    "b200unet_cvo_kern_mat_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P]),
+    "b200unet_cvo_cross_fwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
+    "b200unet_cvo_inner_prod_fwd": (_I, [C.POINTER(CvoItem), _I, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "b200unet_cvo_inner_prod_bwd": (_I, [C.POINTER(CvoItem), _I, _P, _P, _I, _I, _I, _P, _P, C.POINTER(_P), C.POINTER(_P),
+                                         _P, _P, _P]),
 }
 
 _lib = None

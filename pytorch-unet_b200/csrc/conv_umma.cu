@@ -46,7 +46,10 @@ namespace b200 {
 
 constexpr int kUmmaThreads = 352;  // 3 control warps + 8 epilogue warps (two per TMEM lane quarter)
 constexpr int kEpiWarps = 8;
-constexpr int kNA = 2;        // A (activation tile) stages
+constexpr int kNA = 2;        // A (activation tile) stages of a 3x3 convolution: one stage feeds nine taps of MMAs
+constexpr int kMaxNA = 6;     // 1x1 / transposed convolutions: a stage feeds ONE tap (512 MMA cycles at MB = 2), less than the
+                              // L2 round trip of its 32 KB TMA box, so two stages left the tensor pipe 27-35 % busy (ncu,
+                              // profiles/r02_conv_metrics.txt launches 9/12/15/18): they get as many stages as fit
 constexpr int kMaxNB = 8;     // B (weight tile) stages
 constexpr uint32_t kSmemBudget = 188 * 1024;   // A + B stages
 constexpr uint32_t kStageOutBytes = kEpiWarps * 4096;  // epilogue transpose buffers: per warp [32 rows][64 cols] bf16
@@ -74,7 +77,7 @@ struct UmmaArgs {
   const float* bias;
   int relu;
   uint32_t a_stage_bytes, a_tx_bytes;
-  int nb_stages;
+  int nb_stages, na_stages;
 };
 
 struct TileCoord {
@@ -112,13 +115,13 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
-  uint8_t* sB = sA + kNA * a.a_stage_bytes;
+  uint8_t* sB = sA + (uint32_t)a.na_stages * a.a_stage_bytes;
   uint8_t* sOut = sB + (uint32_t)a.nb_stages * B_STAGE_BYTES;
   float* sBias = reinterpret_cast<float*>(sOut + kStageOutBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + kBiasSmemFloats);
   uint64_t* a_full = bars;
-  uint64_t* a_empty = a_full + kNA;
-  uint64_t* b_full = a_empty + kNA;
+  uint64_t* a_empty = a_full + kMaxNA;
+  uint64_t* b_full = a_empty + kMaxNA;
   uint64_t* b_empty = b_full + kMaxNB;
   uint64_t* t_full = b_empty + kMaxNB;
   uint64_t* t_empty = t_full + 2;
@@ -134,7 +137,7 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
   const int work_step = CL == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kNA; ++i) {
+    for (int i = 0; i < kMaxNA; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
     }
@@ -188,7 +191,7 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
               mbar_arrive_expect_tx(&a_full[stage], a.a_tx_bytes);
               tma_load_4d(&maps.a[s], &a_full[stage], sA + stage * a.a_stage_bytes, c0, t.x0 - a.pad, t.y0 - a.pad, t.n);
             }
-            if (++stage == kNA) {
+            if (++stage == a.na_stages) {
               stage = 0;
               phase ^= 1;
             }
@@ -234,7 +237,7 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
     int astage = 0, bstage = 0;
     uint32_t aphase = 0, bphase = 0;
     int it = 0;
-    const int n_taps = a.taps, kx = a.kx, pitch = a.P, n_bstages = a.nb_stages;
+    const int n_taps = a.taps, kx = a.kx, pitch = a.P, n_bstages = a.nb_stages, n_astages = a.na_stages;
     const uint32_t a_stage_bytes = a.a_stage_bytes;
     // CL = 2: the leader issues for the pair; the peer's MMA warp only took part in the TMEM allocation
     for (int tile = (CL == 2 && rank != 0) ? total_tiles : work0; tile < total_tiles; tile += work_step, ++it) {
@@ -295,7 +298,7 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
             if (CL == 2) umma_commit_2cta(&a_empty[astage], (uint16_t)0x3); else umma_commit(&a_empty[astage]);
           }
           __syncwarp();
-          if (++astage == kNA) {
+          if (++astage == n_astages) {
             astage = 0;
             aphase ^= 1;
           }
@@ -532,6 +535,7 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
 // ------------------------------------------------------------------ host side
 // 0 disables the CTA-pair (cta_group::2) variant; B200UNET_NO_CLUSTER=1 in the environment sets it (for A/B timing)
 static int g_umma_cluster = getenv("B200UNET_NO_CLUSTER") ? 0 : 1;
+static int g_umma_deep_a = getenv("B200UNET_NO_DEEP_A") ? 0 : 1;
 static int g_umma_max_mb = getenv("B200UNET_MAX_MB") ? atoi(getenv("B200UNET_MAX_MB")) : 4;
 // N tile: 128 by default.  BN = 256 halves the activation re-reads but needs all 512 TMEM columns for one MB = 2 tile, so
 // the epilogue is not overlapped; once CTA pairs had halved the weight traffic, BN = 128 (double-buffered accumulators)
@@ -542,7 +546,7 @@ struct Plan {
   int MB, BN, CL, P, TH, TW, halo;
   int tiles_x, tiles_y, n_ntiles;
   uint32_t a_stage_bytes, a_tx_bytes, smem_bytes;
-  int nb_stages;
+  int nb_stages, na_stages;
 };
 
 static bool aligned_view(const b200_view& v) {
@@ -642,11 +646,15 @@ static bool make_plan(int Ho, int Wo, int n_img, int halo, int cout_total, int n
   pl->n_ntiles = (cout_total + bn - 1) / bn;
   pl->a_tx_bytes = (uint32_t)(pl->TH + halo) * pl->P * 128;
   const uint32_t b_stage = (uint32_t)(bn / pl->CL) * 128;
-  int nb = (int)((kSmemBudget - 1024 - kNA * pl->a_stage_bytes) / b_stage);
+  int na = kNA;
+  if (halo == 0 && g_umma_deep_a)  // no taps to amortise an A stage over: deepen the A pipeline (B keeps >= 4 stages)
+    while (na < kMaxNA && (uint32_t)(na + 1) * pl->a_stage_bytes + 4 * b_stage + 1024 <= kSmemBudget) ++na;
+  pl->na_stages = na;
+  int nb = (int)((kSmemBudget - 1024 - na * pl->a_stage_bytes) / b_stage);
   if (nb > kMaxNB) nb = kMaxNB;
   if (nb < 2) return false;
   pl->nb_stages = nb;
-  pl->smem_bytes = kNA * pl->a_stage_bytes + nb * b_stage + kStageOutBytes + kBiasSmemFloats * 4 + 1024 /*align*/ +
+  pl->smem_bytes = na * pl->a_stage_bytes + nb * b_stage + kStageOutBytes + kBiasSmemFloats * 4 + 1024 /*align*/ +
                    512 /*barriers*/;
   return true;
 }
@@ -714,6 +722,7 @@ static int launch_plan(const TileMaps& maps, UmmaArgs& a, const Plan& pl, cudaSt
   a.a_stage_bytes = pl.a_stage_bytes;
   a.a_tx_bytes = pl.a_tx_bytes;
   a.nb_stages = pl.nb_stages;
+  a.na_stages = pl.na_stages;
 #define B200_INST(MBv, BNv)                                                                   \
   if (pl.MB == MBv && pl.BN == BNv)                                                           \
     return pl.CL == 2 ? launch_inst<MBv, BNv, 2>(maps, a, pl, st) : launch_inst<MBv, BNv, 1>(maps, a, pl, st);
