@@ -10,7 +10,7 @@ What it restates (plain PyTorch, fp32 or fp64, any device):
   calc_w_v            network_modules.py:1052-1094
 
 PARITY PINNING.  geometry.py's Python and the network_modules.py methods are pinned: oracle/make_golden_cvo.py runs
-the UNMODIFIED reference source for them and tests/test_cvo_oracle.py compares (tests/golden/cvo_*.npz).  The three
+the UNMODIFIED reference source for them and tests/test_cvo_oracle.py compares (tests/golden/cvo/cvo_*.npz).  The three
 CUDA extensions those functions call have NO source in the reference tree (only stale cp36/cp37
 binaries are named in .MISSING_LARGE_BLOBS), so their semantics are restated from the call sites and are
 "parity unpinned":

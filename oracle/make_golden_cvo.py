@@ -1,4 +1,4 @@
-"""Generates tests/golden/cvo_*.npz by running the UNMODIFIED reference source of the CVO Gramian loss (this container
+"""Generates tests/golden/cvo/cvo_*.npz by running the UNMODIFIED reference source of the CVO Gramian loss (this container
 only; /root/reference is read, never copied).  TEST INFRASTRUCTURE ONLY.
 
     python oracle/make_golden_cvo.py
@@ -22,7 +22,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.environ.get("UNET_REFERENCE_DIR", "/root/reference")
-OUT = os.path.join(ROOT, "tests", "golden")
+OUT = os.path.join(ROOT, "tests", "golden", "cvo")
 
 
 def _install_stubs():

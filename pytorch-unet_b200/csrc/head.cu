@@ -5,6 +5,8 @@
 // Thread mapping: 8 lanes cooperate on one pixel, each lane owns one 16-byte vector of every 64-channel chunk,
 // so a warp reads 4 pixels x 128 contiguous bytes per instruction.  blockIdx.y selects the 64-channel chunk whose
 // dx / dW this block produces (the dot product itself always runs over all channels).
+#include <cstdlib>
+
 #include "chan_reduce.cuh"
 
 namespace b200 {
@@ -532,6 +534,266 @@ __global__ void __launch_bounds__(kHeadThreads, 2) head_dense_kernel(HeadArgs a,
   }
 }
 
+// ------------------------------------------------------------------ pixel-per-thread path (bf16 tier, 16 / 32 / 64 channels, <= 4 classes)
+// ncu on head_dense_kernel above (profiles/r02_hbm_metrics.txt): 210-268 M warp instructions per launch, DRAM 28-45 % busy —
+// the kernel is bound by INSTRUCTION ISSUE, not by memory: with 8 lanes per pixel every lane repeats the bias / ReLU /
+// softmax / label logic of its pixel, each dot product ends in a 3-step shuffle tree, and zr[label] went through local
+// memory.  Here a block stages 256 pixels (256 x C bf16, cp.async, 3-stage ring) in shared memory with the 16-byte chunks
+// of a pixel XOR-swizzled by the pixel index, and works on them in two mappings:
+//   pass 1  thread = pixel: reads its own row (conflict-free thanks to the swizzle), one dot product per class with packed
+//           FFMA2 against broadcast weights, softmax / loss / dz ONCE per pixel; dz goes to shared memory;
+//   pass 2  (backward) thread = (16-byte chunk j, pixel subset): its 8 channels' weights and dW accumulators stay in
+//           registers; per pixel one LDS.128 of x and the pixel's dz give dW += dz * x and dx = mask(dz . w), and the 8 lanes
+//           of a pixel store its 128 contiguous bytes of dx.
+// ~200 (forward) / ~700 (backward) thread instructions per pixel instead of ~1400 / ~1800.
+constexpr int kPixStages = 3;
+constexpr int kPixPerBlock = 256;
+
+template <int KMAX, int C, int MODE>
+__global__ void __launch_bounds__(kHeadThreads, 2) head_pix_kernel(HeadArgs a, long long npix) {
+  constexpr int CH = C / 8;                   // 16-byte chunks per pixel
+  constexpr int NS = kHeadThreads / CH;       // pass 2: pixel subsets
+  constexpr int PPS = kPixPerBlock / NS;      // pass 2: pixels per subset (= CH)
+  constexpr bool BWD = MODE == HEAD_BWD || MODE == HEAD_CE_BWD;
+  constexpr bool CE = MODE == HEAD_CE_FWD || MODE == HEAD_CE_BWD;
+  extern __shared__ __align__(16) uint8_t pix_raw[];
+  uint4* ring = reinterpret_cast<uint4*>(pix_raw);                             // [stages][256 pixels][CH]
+  float* sw = reinterpret_cast<float*>(ring + kPixStages * kPixPerBlock * CH);  // [KMAX][C], zero for k >= K
+  float2* sdz = reinterpret_cast<float2*>(sw + KMAX * C);                       // backward: [KMAX][256] as (dz, dz) pairs
+  __shared__ float redw[kHeadThreads / 32][2];
+  const int K = a.k;
+  const int t = threadIdx.x;
+  for (int i = t; i < KMAX * C; i += kHeadThreads) sw[i] = i < K * C ? a.w[i] : 0.f;
+  float bias[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) bias[k] = (k < K && a.b) ? a.b[k] : 0.f;
+  float gs = 1.f;
+  if (MODE == HEAD_CE_BWD) gs = (a.gscale ? a.gscale[0] : 1.f) * a.ce_state[1];
+  const long long hw = (long long)a.x.h * a.x.w;
+  const uint4* __restrict__ xg = reinterpret_cast<const uint4*>(a.x.p);  // dense: pixel p, chunk j at xg[p * CH + j]
+
+  // pass-2 role
+  const int j2 = t % CH, s2 = t / CH;
+  float2 w2[BWD ? KMAX : 1][4], dw2[BWD ? KMAX : 1][4];
+  float db_acc[KMAX];
+  float loss_acc = 0.f, cnt_acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) db_acc[k] = 0.f;
+  if (BWD) {
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        w2[k][e] = k < K ? make_float2(a.w[k * C + j2 * 8 + 2 * e], a.w[k * C + j2 * 8 + 2 * e + 1]) : make_float2(0.f, 0.f);
+        dw2[k][e] = make_float2(0.f, 0.f);
+      }
+  }
+
+  const long long nchunks = (npix + kPixPerBlock - 1) / kPixPerBlock;
+  auto issue = [&](long long chunk, int stage) {
+    if (chunk < nchunks) {
+      const long long p0 = chunk * kPixPerBlock;
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        const int g = i * kHeadThreads + t;        // 16-byte piece of the block's 256 * CH, coalesced
+        const int pl = g / CH, j = g - pl * CH;
+        if (p0 + pl < npix)
+          cp_async_16(&ring[(stage * kPixPerBlock + pl) * CH + (j ^ (pl & (CH - 1)))], xg + (p0 + pl) * CH + j);
+      }
+    }
+    cp_async_commit();
+  };
+  long long chunk = blockIdx.x;
+#pragma unroll
+  for (int st = 0; st < kPixStages - 1; ++st) issue(chunk + (long long)st * gridDim.x, st);
+  int stage = 0;
+  for (; chunk < nchunks; chunk += gridDim.x) {
+    issue(chunk + (long long)(kPixStages - 1) * gridDim.x, stage == 0 ? kPixStages - 1 : stage - 1);
+    cp_async_wait<kPixStages - 1>();
+    __syncthreads();  // every thread's pieces of this stage have landed (and sw on the first iteration)
+    const long long p0 = chunk * kPixPerBlock;
+    const uint4* rows = ring + stage * kPixPerBlock * CH;
+    // ---------------- pass 1: thread = pixel
+    {
+      const long long p = p0 + t;
+      const bool live = p < npix;
+      float2 acc[KMAX];
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) acc[k] = make_float2(0.f, 0.f);
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          const uint4 v = rows[t * CH + (j ^ (t & (CH - 1)))];
+          const float2 x01 = bf2x_to_f2(v.x), x23 = bf2x_to_f2(v.y), x45 = bf2x_to_f2(v.z), x67 = bf2x_to_f2(v.w);
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) {
+            const float4 wa = *reinterpret_cast<const float4*>(sw + k * C + j * 8);
+            const float4 wb = *reinterpret_cast<const float4*>(sw + k * C + j * 8 + 4);
+            acc[k] = ffma2(x01, make_float2(wa.x, wa.y), acc[k]);
+            acc[k] = ffma2(x23, make_float2(wa.z, wa.w), acc[k]);
+            acc[k] = ffma2(x45, make_float2(wb.x, wb.y), acc[k]);
+            acc[k] = ffma2(x67, make_float2(wb.z, wb.w), acc[k]);
+          }
+        }
+      }
+      float z[KMAX], zr[KMAX];
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        z[k] = acc[k].x + acc[k].y + bias[k];
+        zr[k] = a.relu ? fmaxf(z[k], 0.f) : z[k];
+      }
+      long long n = 0, r = 0;
+      if ((!BWD && a.logits) || MODE == HEAD_BWD) {
+        n = p / hw;
+        r = p - n * hw;
+      }
+      if (!BWD && a.logits && live) {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+          if (k < K) a.logits[(n * K + k) * hw + r] = zr[k];
+      }
+      if (MODE != HEAD_FWD) {
+        int lab = -1;  // class, -1 = ignore_index, -2 = out of range
+        bool valid = live;
+        float lse = 0.f;
+        if (CE) {
+          if (live) {
+            const long long l64 = a.labels[p];
+            lab = l64 == kIgnoreIndex ? -1 : ((l64 < 0 || l64 >= K) ? -2 : (int)l64);
+          }
+          valid = live && lab != -1;
+          float m = -INFINITY;
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k)
+            if (k < K) m = fmaxf(m, zr[k]);
+          float sum = 0.f;
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k)
+            if (k < K) sum += __expf(zr[k] - m);
+          lse = m + __logf(sum);
+        }
+        if (MODE == HEAD_CE_FWD) {
+          if (valid) {
+            float zy = 0.f;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) zy = k == lab ? zr[k] : zy;
+            if (lab == -2) zy = __int_as_float(0x7fc00000);  // out-of-range label: poison the loss
+            loss_acc += lse - zy;
+            cnt_acc += 1.f;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) {
+            float g = 0.f;
+            if (k < K && valid) {
+              if (MODE == HEAD_CE_BWD) g = gs * (__expf(zr[k] - lse) - (k == lab ? 1.f : 0.f));
+              else g = a.dlogits[(n * K + k) * hw + r];
+              if (a.relu && !(z[k] > 0.f)) g = 0.f;
+            }
+            sdz[k * kPixPerBlock + t] = make_float2(g, g);
+          }
+        }
+      }
+    }
+    if (BWD) {
+      __syncthreads();  // dz of the 256 pixels
+      // ---------------- pass 2: thread = (chunk j2, subset s2); pixel pl = i * NS + s2 -> the 32 lanes of a warp cover
+      // 32 / CH consecutive pixels x all chunks: one contiguous run of dx per store instruction
+      uint4* dxg = reinterpret_cast<uint4*>(a.dx.p);
+#pragma unroll
+      for (int i = 0; i < PPS; ++i) {
+        const int pl = i * NS + s2;
+        if (p0 + pl < npix) {
+          const uint4 v = rows[pl * CH + (j2 ^ (pl & (CH - 1)))];
+          float2 x2[4] = {bf2x_to_f2(v.x), bf2x_to_f2(v.y), bf2x_to_f2(v.z), bf2x_to_f2(v.w)};
+          float2 r2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) {
+            const float2 d = sdz[k * kPixPerBlock + pl];
+            if (j2 == 0) db_acc[k] += d.x;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              dw2[k][e] = ffma2(d, x2[e], dw2[k][e]);
+              r2[e] = ffma2(d, w2[k][e], r2[e]);
+            }
+          }
+          if (dxg) {
+            if (a.mask) {  // the mask IS x here (no BatchNorm): ReLU backward of the last convolution
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                r2[e].x = x2[e].x > 0.f ? r2[e].x : 0.f;
+                r2[e].y = x2[e].y > 0.f ? r2[e].y : 0.f;
+              }
+            }
+            dxg[(p0 + pl) * CH + j2] = make_uint4(f2_to_bf2x(r2[0].x, r2[0].y), f2_to_bf2x(r2[1].x, r2[1].y),
+                                                  f2_to_bf2x(r2[2].x, r2[2].y), f2_to_bf2x(r2[3].x, r2[3].y));
+          }
+        }
+      }
+    }
+    __syncthreads();  // this stage (and sdz) may be overwritten
+    stage = stage + 1 == kPixStages ? 0 : stage + 1;
+  }
+  cp_async_wait<0>();
+  if (MODE == HEAD_FWD) return;
+  __syncthreads();
+  const int warp = t >> 5, lane = t & 31;
+  if (MODE == HEAD_CE_FWD) {
+    loss_acc = warp_sum(loss_acc);
+    cnt_acc = warp_sum(cnt_acc);
+    if (lane == 0) {
+      redw[warp][0] = loss_acc;
+      redw[warp][1] = cnt_acc;
+    }
+    __syncthreads();
+    if (t == 0) {
+      float l = 0.f, cn = 0.f;
+      for (int wdx = 0; wdx < kHeadThreads / 32; ++wdx) {
+        l += redw[wdx][0];
+        cn += redw[wdx][1];
+      }
+      a.ws[blockIdx.x * 2 + 0] = l;
+      a.ws[blockIdx.x * 2 + 1] = cn;
+    }
+    return;
+  }
+  if (BWD) {
+    // reduce over the NS pixel subsets through the (now idle) ring: red[s2][k][c], then [s2][K] for db
+    float* red = reinterpret_cast<float*>(pix_raw);
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        red[(s2 * KMAX + k) * C + j2 * 8 + 2 * e] = dw2[k][e].x;
+        red[(s2 * KMAX + k) * C + j2 * 8 + 2 * e + 1] = dw2[k][e].y;
+      }
+    float* redb = red + NS * KMAX * C;
+    if (j2 == 0) {
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) redb[s2 * KMAX + k] = db_acc[k];
+    }
+    __syncthreads();
+    float* out = a.ws + (long long)blockIdx.x * (K * C + K);
+    for (int q = t; q < K * C; q += kHeadThreads) {
+      float sacc = 0.f;
+      for (int s = 0; s < NS; ++s) sacc += red[s * KMAX * C + q];  // q = k * C + c with k < K <= KMAX
+      out[q] = sacc;
+    }
+    if (t < K) {
+      float sacc = 0.f;
+      for (int s = 0; s < NS; ++s) sacc += redb[s * KMAX + t];
+      out[K * C + t] = sacc;
+    }
+  }
+}
+
+inline size_t head_pix_smem(int c, int kmax, bool bwd) {
+  const size_t ring = (size_t)kPixStages * kPixPerBlock * c * 2;
+  const size_t tail = (size_t)kmax * c * 4 + (bwd ? (size_t)kmax * kPixPerBlock * 8 : 0);
+  const size_t red = bwd ? (size_t)(kHeadThreads / (c / 8)) * kmax * (c + 1) * 4 : 0;  // aliases the ring after the loop
+  return (ring > red ? ring : red) + tail;
+}
+
 inline bool dense_nhwc(const DView& v) {
   return v.sw == v.c && v.sh == (long long)v.w * v.sw && v.sn == (long long)v.h * v.sh;
 }
@@ -613,8 +875,48 @@ __global__ void head_bwd_finalize_kernel(const float* __restrict__ ws, int block
     db[q - kc] = (float)s;
 }
 
+template <int MODE, int KMAX, int CC>
+void launch_head_pix_inst(const HeadArgs& a, int blocks, long long npix, cudaStream_t st) {
+  constexpr bool BWD = MODE == HEAD_BWD || MODE == HEAD_CE_BWD;
+  const size_t smem = head_pix_smem(CC, KMAX, BWD);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(head_pix_kernel<KMAX, CC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_done = true;
+  }
+  head_pix_kernel<KMAX, CC, MODE><<<blocks, kHeadThreads, smem, st>>>(a, npix);
+}
+
+static int g_head_pix = getenv("B200UNET_NO_HEAD_PIX") ? 0 : 1;
+
+// returns true if the pixel-per-thread kernel took the launch
+template <int MODE>
+bool launch_head_pix(const HeadArgs& a, int* blocks_io, cudaStream_t st) {
+  constexpr bool BWD = MODE == HEAD_BWD || MODE == HEAD_CE_BWD;
+  const int c = a.x.c, K = a.k;
+  if (!g_head_pix || !(c == 16 || c == 32 || c == 64) || K > 4 || a.x.lo || !dense_nhwc(a.x)) return false;
+  if (reinterpret_cast<uintptr_t>(a.x.p) % 16) return false;
+  if (BWD) {
+    if (a.dx.p && (!dense_nhwc(a.dx) || reinterpret_cast<uintptr_t>(a.dx.p) % 16)) return false;
+    if (a.mask && a.mask != a.x.p) return false;  // a separate mask tensor (BatchNorm graphs): general kernel
+  }
+  const long long npix = (long long)a.x.n * a.x.h * a.x.w;
+  long long blocks = (npix + kPixPerBlock - 1) / kPixPerBlock;
+  if (blocks > 2 * kNumSMsB200) blocks = 2 * kNumSMsB200;  // persistent: two blocks per SM
+  if (blocks < 1) blocks = 1;
+  *blocks_io = (int)blocks;
+  const int kmax = K <= 2 ? 2 : 4;
+#define B200_HP(KM, CC) launch_head_pix_inst<MODE, KM, CC>(a, (int)blocks, npix, st)
+  if (c == 64) { if (kmax == 2) B200_HP(2, 64); else B200_HP(4, 64); }
+  else if (c == 32) { if (kmax == 2) B200_HP(2, 32); else B200_HP(4, 32); }
+  else { if (kmax == 2) B200_HP(2, 16); else B200_HP(4, 16); }
+#undef B200_HP
+  return true;
+}
+
 template <int MODE>
 int launch_head(const HeadArgs& a, int* blocks_io, cudaStream_t st) {
+  if (launch_head_pix<MODE>(a, blocks_io, st)) return check_launch("head (pixel-per-thread)");
   if (launch_head_dense<MODE>(a, blocks_io, st)) return check_launch("head (dense)");
   const int blocks = *blocks_io;
   const int c = a.x.c, K = a.k;

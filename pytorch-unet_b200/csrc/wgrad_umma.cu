@@ -467,7 +467,7 @@ static bool wg_aligned(const b200_view& v) {
 
 static bool wg_device_ok() {
   static int cached = -1;
-  if (cached < 0) cached = b200unet_device_ok();
+  if (cached < 0) cached = (getenv("B200UNET_PLAN_ONLY") != nullptr) ? 1 : b200unet_device_ok();  // plan dumps without a GPU
   return cached == 1;
 }
 

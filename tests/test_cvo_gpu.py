@@ -12,7 +12,7 @@ import torch
 from oracle import cvo_oracle as CO
 
 pytestmark = pytest.mark.gpu
-GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cvo")
 
 
 def _g(a, grad=False):

@@ -8,7 +8,7 @@ import torch
 
 from oracle import cvo_oracle as CO
 
-GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cvo")
 
 
 def _t(a, grad=False):
