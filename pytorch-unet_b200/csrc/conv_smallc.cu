@@ -14,29 +14,24 @@ namespace b200 {
 
 constexpr int kScThreads = 256;
 
-// Strip geometry of the forward kernel: a block iteration covers R output rows x (4 * gseg) output columns
-// (R * gseg <= 64 pixel groups of 4 = one group per 4 lanes), chosen on the host to waste the fewest lanes.
-struct ScStrip {
-  int R, gseg, segs_per_row, strips_per_img_col;  // strips_per_img_col = ceil(h / R)
-};
+// Forward.  ncu on the first version (profiles/r02_hbm_metrics.txt): 313 M warp instructions per launch and an issue rate of
+// 0.6 — every one of the 4 lanes of a pixel group fetched the 18 input values itself (64-bit index arithmetic + bounds
+// tests per value), bias and ReLU were separate fp32 passes over the 64 accumulators, and each FFMA2 needed its input
+// duplicated into a register pair.  A second version staged the window per BLOCK behind a barrier and was no faster: two
+// blocks per SM, both regularly parked in the load -> store -> barrier sequence (ncu: issue 0.42, stalls long-scoreboard /
+// barrier / wait).  Now every WARP owns 32 consecutive output pixels of one row: its 3 x 34 input window lives in a
+// warp-private, double-buffered shared-memory slab as (x, x) pairs (one LDS.128 = two FFMA2 operands); the window of the
+// warp's NEXT unit is loaded into registers before the FMAs of the current one and parked afterwards (__syncwarp only, no
+// block barrier), the accumulators start from the bias, and ReLU is the .relu of the bf16x2 conversion.
+constexpr int kScPitch = 36;  // float2 per staged row: 34 used, rows stay 16-byte aligned
 
-// Forward.  ncu on the first version (profiles/r02_hbm_metrics.txt): 313 M warp instructions per launch = issue-bound
-// (0.49 ms against 0.2 ms of HBM time) — every one of the 4 lanes of a pixel group fetched the 18 input values itself
-// (64-bit index arithmetic + bounds tests per value), bias and ReLU were separate fp32 passes over the 64 accumulators,
-// and each FFMA2 needed its input duplicated into a register pair.  Now the (R+2) x (4 gseg + 2) input window of a strip is
-// staged ONCE per block in shared memory, already duplicated as (x, x) pairs (one LDS.128 = two FFMA2 operands, no MOVs),
-// double-buffered (one barrier per strip); the accumulators start from the bias and ReLU is the .relu of the bf16x2
-// conversion.
 template <int CIN>
 __global__ void __launch_bounds__(kScThreads, 2)
-smallc_fwd_kernel(DView src, DView dst, const float* __restrict__ w, const float* __restrict__ bias, int relu, int pad,
-                  ScStrip sp) {
-  extern __shared__ __align__(16) float sc_smem[];
-  float* ws = sc_smem;                      // [9 * CIN][64]
-  float* bs = ws + 9 * CIN * 64;            // [64]
-  float2* xs = reinterpret_cast<float2*>(bs + 64);  // [2][(R + 2) * CIN][wcols] as (x, x) pairs
-  const int wcols = 4 * sp.gseg + 4;        // 4 gseg + 2 used, padded so that rows stay 16-byte aligned
-  const int xrows = (sp.R + 2) * CIN;
+smallc_fwd_kernel(DView src, DView dst, const float* __restrict__ w, const float* __restrict__ bias, int relu, int pad) {
+  __shared__ __align__(16) float ws[9 * CIN * 64];
+  __shared__ __align__(16) float bs[64];
+  extern __shared__ __align__(16) uint8_t sc_dyn[];
+  float2 (*xs)[2][3 * CIN][kScPitch] = reinterpret_cast<float2 (*)[2][3 * CIN][kScPitch]>(sc_dyn);  // [warp][buffer][row][column]
   const int cout = dst.c;
   const int o_base = blockIdx.y * 64;
   for (int i = threadIdx.x; i < 9 * CIN * 64; i += kScThreads) {
@@ -45,49 +40,64 @@ smallc_fwd_kernel(DView src, DView dst, const float* __restrict__ w, const float
     ws[i] = (o_base + o < cout) ? w[((long long)(o_base + o) * CIN + c) * 9 + tap] : 0.f;
   }
   if (threadIdx.x < 64) bs[threadIdx.x] = (bias && o_base + threadIdx.x < cout) ? bias[o_base + threadIdx.x] : 0.f;
+  __syncthreads();
 
-  const int q4 = threadIdx.x & 3;
-  const int g = threadIdx.x >> 2;
-  const int rr = g / sp.gseg, gx = g - rr * sp.gseg;
-  const bool lane_on = rr < sp.R && o_base + q4 * 8 < cout;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q4 = lane & 3, g = lane >> 2;
+  const bool lane_on = o_base + q4 * 8 < cout;
   const bool second_half = o_base + 32 + q4 * 8 < cout;  // cout is a multiple of 16, not necessarily of 64
-  const int strips_per_img = sp.strips_per_img_col * sp.segs_per_row;
-  const long long total = (long long)dst.n * strips_per_img;
+  const unsigned segs = (unsigned)(dst.w + 31) / 32;
+  const unsigned total = (unsigned)dst.n * dst.h * segs;
+  const unsigned step = gridDim.x * (kScThreads / 32);
 
-  auto stage = [&](long long strip, int buf) {
-    const int n = (int)(strip / strips_per_img);
-    const int rem = (int)(strip - (long long)n * strips_per_img);
-    const int ys = rem / sp.segs_per_row, xsg = rem - ys * sp.segs_per_row;
-    const int y0 = ys * sp.R - pad, x0 = xsg * sp.gseg * 4 - pad;
-    float2* xb = xs + (size_t)buf * xrows * wcols;
-    const int ncol = 4 * sp.gseg + 2;
-    for (int e = threadIdx.x; e < xrows * ncol; e += kScThreads) {
-      const int row = e / ncol, col = e - row * ncol;
-      const int r = row / CIN, c = row - r * CIN;
-      const int iy = y0 + r, ix = x0 + col;
-      float v = 0.f;
-      if (iy >= 0 && iy < src.h && ix >= 0 && ix < src.w) {
-        const long long so = src.off(n, iy, ix) + c;
-        v = bf2f(src.p[so]);
-        if (src.lo) v += bf2f(src.lo[so]);  // split tier: the image is carried as hi + lo
+  // the window of a unit: rows oy - pad .. +2, columns seg * 32 - pad .. +33; lane l fetches column l, lanes 0 / 1 also 32 / 33
+  float v[3 * CIN][2];
+  auto fetch = [&](unsigned unit) {
+    const unsigned seg = unit % segs, t = unit / segs;
+    const int oy = (int)(t % dst.h), n = (int)(t / dst.h);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int iy = oy + r - pad;
+      const bool yok = iy >= 0 && iy < src.h;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int ix = (int)seg * 32 + lane + 32 * e - pad;
+        const bool ok = yok && ix >= 0 && ix < src.w && (e == 0 || lane < 2);
+        const long long so = ok ? src.off(n, iy, ix) : 0;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
+          float x = 0.f;
+          if (ok) {
+            x = bf2f(src.p[so + c]);
+            if (src.lo) x += bf2f(src.lo[so + c]);  // split tier: the image is carried as hi + lo
+          }
+          v[r * CIN + c][e] = x;
+        }
       }
-      xb[row * wcols + col] = make_float2(v, v);
+    }
+  };
+  auto park = [&](int buf) {
+#pragma unroll
+    for (int rc = 0; rc < 3 * CIN; ++rc) {
+      xs[warp][buf][rc][lane] = make_float2(v[rc][0], v[rc][0]);
+      if (lane < 2) xs[warp][buf][rc][32 + lane] = make_float2(v[rc][1], v[rc][1]);
     }
   };
 
-  long long strip = blockIdx.x;
+  unsigned unit = blockIdx.x * (kScThreads / 32) + warp;
   int buf = 0;
-  if (strip < total) stage(strip, 0);
-  __syncthreads();  // weights + first window
-  for (; strip < total; strip += gridDim.x, buf ^= 1) {
-    const long long next = strip + gridDim.x;
-    if (next < total) stage(next, buf ^ 1);  // the other buffer was last read before the previous barrier
-    const int n = (int)(strip / strips_per_img);
-    const int rem = (int)(strip - (long long)n * strips_per_img);
-    const int ys = rem / sp.segs_per_row, xsg = rem - ys * sp.segs_per_row;
-    const int oy = ys * sp.R + rr;
-    const int ox0 = (xsg * sp.gseg + gx) * 4;
-    if (lane_on && oy < dst.h && ox0 < dst.w) {
+  if (unit < total) {
+    fetch(unit);
+    park(0);
+  }
+  __syncwarp();
+  for (; unit < total; unit += step, buf ^= 1) {
+    const bool more = unit + step < total;
+    if (more) fetch(unit + step);  // in flight during the FMAs below
+    const unsigned seg = unit % segs, t = unit / segs;
+    const int oy = (int)(t % dst.h), n = (int)(t / dst.h);
+    const int ox0 = (int)seg * 32 + g * 4;
+    if (lane_on && ox0 < dst.w) {
       float2 acc[4][8];  // 4 pixels x 16 channels as fp32 pairs: FFMA2 does two channels per instruction
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -95,32 +105,31 @@ smallc_fwd_kernel(DView src, DView dst, const float* __restrict__ w, const float
 #pragma unroll
         for (int p = 0; p < 4; ++p) acc[p][k] = b2;
       }
-      const float2* xb = xs + (size_t)buf * xrows * wcols + gx * 4;
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
 #pragma unroll
         for (int c = 0; c < CIN; ++c) {
           float2 xin[6];
-          const float4* xp = reinterpret_cast<const float4*>(xb + ((rr + r) * CIN + c) * wcols);
+          const float4* xp = reinterpret_cast<const float4*>(&xs[warp][buf][r * CIN + c][g * 4]);
 #pragma unroll
           for (int j = 0; j < 3; ++j) {
-            const float4 t = xp[j];
-            xin[2 * j] = make_float2(t.x, t.y);
-            xin[2 * j + 1] = make_float2(t.z, t.w);
+            const float4 tt = xp[j];
+            xin[2 * j] = make_float2(tt.x, tt.y);
+            xin[2 * j + 1] = make_float2(tt.z, tt.w);
           }
 #pragma unroll
-          for (int s = 0; s < 3; ++s) {
+          for (int sx = 0; sx < 3; ++sx) {
             // lane q4 owns channels [8 q4, 8 q4 + 8) and [32 + 8 q4, 32 + 8 q4 + 8): the four lanes of a pixel then write
             // two contiguous 64-byte runs (full 32-byte sectors per store instruction)
-            const float* wp = ws + ((r * 3 + s) * CIN + c) * 64 + q4 * 8;
+            const float* wp = ws + ((r * 3 + sx) * CIN + c) * 64 + q4 * 8;
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
               const float4 wv = *reinterpret_cast<const float4*>(wp + (j4 >> 1) * 32 + (j4 & 1) * 4);
               const float2 w01 = make_float2(wv.x, wv.y), w23 = make_float2(wv.z, wv.w);
 #pragma unroll
               for (int p = 0; p < 4; ++p) {
-                acc[p][j4 * 2 + 0] = ffma2(xin[p + s], w01, acc[p][j4 * 2 + 0]);
-                acc[p][j4 * 2 + 1] = ffma2(xin[p + s], w23, acc[p][j4 * 2 + 1]);
+                acc[p][j4 * 2 + 0] = ffma2(xin[p + sx], w01, acc[p][j4 * 2 + 0]);
+                acc[p][j4 * 2 + 1] = ffma2(xin[p + sx], w23, acc[p][j4 * 2 + 1]);
               }
             }
           }
@@ -135,19 +144,19 @@ smallc_fwd_kernel(DView src, DView dst, const float* __restrict__ w, const float
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             if (h == 1 && !second_half) break;
-            uint4 c;
+            uint4 cc;
             if (relu) {
-              c.x = pack_bf16x2_relu(acc[p][4 * h + 0].x, acc[p][4 * h + 0].y);
-              c.y = pack_bf16x2_relu(acc[p][4 * h + 1].x, acc[p][4 * h + 1].y);
-              c.z = pack_bf16x2_relu(acc[p][4 * h + 2].x, acc[p][4 * h + 2].y);
-              c.w = pack_bf16x2_relu(acc[p][4 * h + 3].x, acc[p][4 * h + 3].y);
+              cc.x = pack_bf16x2_relu(acc[p][4 * h + 0].x, acc[p][4 * h + 0].y);
+              cc.y = pack_bf16x2_relu(acc[p][4 * h + 1].x, acc[p][4 * h + 1].y);
+              cc.z = pack_bf16x2_relu(acc[p][4 * h + 2].x, acc[p][4 * h + 2].y);
+              cc.w = pack_bf16x2_relu(acc[p][4 * h + 3].x, acc[p][4 * h + 3].y);
             } else {
-              c.x = pack_bf16x2(acc[p][4 * h + 0].x, acc[p][4 * h + 0].y);
-              c.y = pack_bf16x2(acc[p][4 * h + 1].x, acc[p][4 * h + 1].y);
-              c.z = pack_bf16x2(acc[p][4 * h + 2].x, acc[p][4 * h + 2].y);
-              c.w = pack_bf16x2(acc[p][4 * h + 3].x, acc[p][4 * h + 3].y);
+              cc.x = pack_bf16x2(acc[p][4 * h + 0].x, acc[p][4 * h + 0].y);
+              cc.y = pack_bf16x2(acc[p][4 * h + 1].x, acc[p][4 * h + 1].y);
+              cc.z = pack_bf16x2(acc[p][4 * h + 2].x, acc[p][4 * h + 2].y);
+              cc.w = pack_bf16x2(acc[p][4 * h + 3].x, acc[p][4 * h + 3].y);
             }
-            *reinterpret_cast<uint4*>(dst.p + oo + 32 * h) = c;
+            *reinterpret_cast<uint4*>(dst.p + oo + 32 * h) = cc;
           }
         } else {
           float f0[8], f1[8];
@@ -170,7 +179,8 @@ smallc_fwd_kernel(DView src, DView dst, const float* __restrict__ w, const float
         }
       }
     }
-    __syncthreads();  // the next window is staged; this one may be overwritten in the next iteration
+    if (more) park(buf ^ 1);  // the other slab was last read one iteration ago, before the __syncwarp below
+    __syncwarp();
   }
 }
 
@@ -331,45 +341,22 @@ bool smallc_conv_fwd_ok(const b200_conv_fwd_params* p) {
   return p->num_src == 1 && p->taps == 9 && p->src[0].c >= 1 && p->src[0].c <= 4 && sc_aligned_out(p->dst) && p->w_f32;
 }
 
-static ScStrip sc_plan_strip(int h, int w) {
-  const int G = (w + 3) / 4;  // pixel groups per row
-  ScStrip best{1, G < 64 ? G : 64, 1, h};
-  double best_eff = -1.0;
-  for (int k = 1; k <= G; ++k) {
-    const int gseg = (G + k - 1) / k;
-    if (gseg > 64) continue;
-    int R = 64 / gseg;
-    if (R > 4) R = 4;   // (R + 2) staged rows per R computed ones
-    if (R > h) R = h;
-    const double lanes = (double)G / ((double)k * gseg) * ((double)R * gseg / 64.0);
-    const double rows = (double)h / ((double)((h + R - 1) / R) * R);
-    const double eff = lanes * rows * (R / (R + 0.25));  // mild preference for taller strips (less staging per output)
-    if (eff > best_eff + 1e-9) {
-      best_eff = eff;
-      best = ScStrip{R, gseg, k, (h + R - 1) / R};
-    }
-    if (gseg == 1) break;
-  }
-  return best;
-}
-
 template <int CIN>
 static int sc_fwd_launch(const b200_conv_fwd_params* p, cudaStream_t st) {
-  const ScStrip sp = sc_plan_strip(p->dst.h, p->dst.w);
-  const long long strips = (long long)p->dst.n * sp.strips_per_img_col * sp.segs_per_row;
-  long long gx = strips < 2 * kNumSMsB200 ? strips : 2 * kNumSMsB200;  // persistent: 2 blocks per SM
+  const long long units = (long long)p->dst.n * p->dst.h * ((p->dst.w + 31) / 32);  // one warp iteration each
+  if (units >= (1LL << 32)) return fail(-1, "smallc_fwd: more than 2^32 row segments");
+  long long gx = (units + kScThreads / 32 - 1) / (kScThreads / 32);
+  if (gx > 2 * kNumSMsB200) gx = 2 * kNumSMsB200;  // persistent: 2 blocks per SM
   dim3 grid((unsigned)gx, (unsigned)((p->dst.c + 63) / 64));
-  const size_t smem = (size_t)(9 * CIN * 64 + 64) * sizeof(float) +
-                      (size_t)2 * (sp.R + 2) * CIN * (4 * sp.gseg + 4) * sizeof(float2);
+  const size_t smem = (size_t)(kScThreads / 32) * 2 * 3 * CIN * kScPitch * sizeof(float2);
   auto kern = smallc_fwd_kernel<CIN>;
   static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  if (!attr_done && smem > 32 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "smallc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_done = true;
   }
-  if (smem > 96 * 1024) return fail(-1, "smallc_fwd: shared-memory window too large (%zu B)", smem);
-  kern<<<grid, kScThreads, smem, st>>>(dview(p->src[0]), dview(p->dst), p->w_f32, p->bias, p->relu, p->pad, sp);
+  kern<<<grid, kScThreads, smem, st>>>(dview(p->src[0]), dview(p->dst), p->w_f32, p->bias, p->relu, p->pad);
   return check_launch("smallc_fwd");
 }
 

@@ -305,6 +305,31 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
       : "memory");
 }
 
+
+// A-operand collector reuse.  Consecutive MMAs that read the SAME A slice (backward-weights: one K slice of the row operand
+// against several filter taps) can keep it in the tensor core's collector buffer instead of fetching it from shared memory
+// again: fill = fetch and keep, use = reuse and keep, lastuse = reuse and release.  (SASS: UTCHMMA gdesc[..].A_KEEP /
+// .A_REUSE.)  An M = 128, N = 128, K = 16 MMA otherwise reads 4 KB of A + 4 KB of B in its 64 cycles = all 128 B/cycle of
+// shared-memory bandwidth, with the TMA fills competing for the same port.
+enum { UMMA_A_DISCARD = 0, UMMA_A_FILL = 1, UMMA_A_USE = 2, UMMA_A_LASTUSE = 3 };
+#define B200_UMMA_COLL(NAME, GROUP, QUAL)                                                                         \
+  __device__ __forceinline__ void NAME(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,         \
+                                       uint32_t accumulate) {                                                     \
+    asm volatile(                                                                                                 \
+        "{\n\t.reg .pred p;\n\t"                                                                                  \
+        "setp.ne.b32 p, %4, 0;\n\t"                                                                               \
+        "tcgen05.mma.cta_group::" GROUP ".kind::f16" QUAL " [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),           \
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)                                                     \
+        : "memory");                                                                                              \
+  }
+B200_UMMA_COLL(umma_bf16_fill, "1", ".collector::a::fill")
+B200_UMMA_COLL(umma_bf16_use, "1", ".collector::a::use")
+B200_UMMA_COLL(umma_bf16_lastuse, "1", ".collector::a::lastuse")
+B200_UMMA_COLL(umma_bf16_2cta_fill, "2", ".collector::a::fill")
+B200_UMMA_COLL(umma_bf16_2cta_use, "2", ".collector::a::use")
+B200_UMMA_COLL(umma_bf16_2cta_lastuse, "2", ".collector::a::lastuse")
+#undef B200_UMMA_COLL
+
 // ------------------------------------------------------------------ UMMA descriptors
 // Shared-memory matrix descriptor (64 bit). Fields (PTX ISA "matrix descriptor", sm_100):
 //   [0,14)  start address >> 4        [16,30) leading-dim byte offset >> 4

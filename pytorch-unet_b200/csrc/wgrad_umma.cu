@@ -65,10 +65,12 @@ struct WgArgs {
   float* ws;
   float* ws_bias;  // [splits][m_pad]
   uint32_t r_blk_bytes, g_tile_bytes, g_box_bytes, stage_bytes;
+  uint32_t r_region_bytes;  // row-operand part of a stage: two 64-channel blocks, or (paired) one block + one more row
   int stages;
   int r_blocks;  // 64-channel blocks of the row operand actually loaded (1 or 2)
   int cta2;      // CTA pairs (see header): cluster of 2, rank = parity of the M block
   int m_units;   // M blocks (cta2: pairs of M blocks) enumerated by the work items
+  int collector; // reuse the row-operand K slice across the MMAs of a K step (A collector buffer)
 };
 
 struct WgItem {
@@ -103,6 +105,64 @@ __device__ __forceinline__ WgItem decode_item(const WgArgs& a, int item, int ran
   w.tile0 = (int)(total * w.split / a.splits);
   w.tile1 = (int)(total * (w.split + 1) / a.splits);
   return w;
+}
+
+// Issues the MMAs of one pipeline stage (one pixel tile): K step outermost, so that the NT filter taps [+ the bias column]
+// of a K slice follow each other and share the slice of the row operand through the A collector buffer.  Everything about
+// the sequence is a compile-time constant (the issuing lane has 48-96 cycles per MMA: a handful of uniform-datapath
+// instructions, no branches).
+template <int MODE, bool CTA2>
+__device__ __forceinline__ void wg_mma(uint32_t d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  if (CTA2) {
+    if (MODE == UMMA_A_FILL) umma_bf16_2cta_fill(d, a_desc, b_desc, idesc, acc);
+    else if (MODE == UMMA_A_USE) umma_bf16_2cta_use(d, a_desc, b_desc, idesc, acc);
+    else if (MODE == UMMA_A_LASTUSE) umma_bf16_2cta_lastuse(d, a_desc, b_desc, idesc, acc);
+    else umma_bf16_2cta(d, a_desc, b_desc, idesc, acc);
+  } else {
+    if (MODE == UMMA_A_FILL) umma_bf16_fill(d, a_desc, b_desc, idesc, acc);
+    else if (MODE == UMMA_A_USE) umma_bf16_use(d, a_desc, b_desc, idesc, acc);
+    else if (MODE == UMMA_A_LASTUSE) umma_bf16_lastuse(d, a_desc, b_desc, idesc, acc);
+    else umma_bf16(d, a_desc, b_desc, idesc, acc);
+  }
+}
+template <int NT, int BIAS, bool CTA2>
+__device__ __forceinline__ void wg_issue_tile(uint32_t tmem_base, int nbw, uint64_t r_desc, uint64_t g_desc0,
+                                              const uint32_t (&goff)[6], uint64_t ones_desc, uint32_t idesc,
+                                              uint32_t idesc_bias, int ksteps, uint32_t accum, bool coll_on) {
+  constexpr int USERS = NT + BIAS;
+  if (USERS > 1 && coll_on) {
+#pragma unroll 2
+    for (int k = 0; k < ksteps; ++k) {
+      // one K step = 16 pixel rows = 2048 B = 128 in the descriptor's (address >> 4) field
+      const uint64_t r_k = r_desc + (uint64_t)k * 128, g_k = g_desc0 + (uint64_t)k * 128;
+      const uint32_t acc_k = k == 0 ? accum : 1u;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const uint32_t d = tmem_base + j * nbw;
+        if (j == 0) wg_mma<UMMA_A_FILL, CTA2>(d, r_k, g_k + goff[j], idesc, acc_k);
+        else if (j == USERS - 1) wg_mma<UMMA_A_LASTUSE, CTA2>(d, r_k, g_k + goff[j], idesc, acc_k);
+        else wg_mma<UMMA_A_USE, CTA2>(d, r_k, g_k + goff[j], idesc, acc_k);
+      }
+      if (BIAS) wg_mma<UMMA_A_LASTUSE, CTA2>(tmem_base + kWgBiasCol, r_k, ones_desc, idesc_bias, acc_k);
+    }
+  } else {
+    // tap outermost (consecutive MMAs accumulate into the same TMEM block), no operand reuse
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const uint64_t g_desc = g_desc0 + goff[j];
+      const uint32_t d = tmem_base + j * nbw;
+      wg_mma<UMMA_A_DISCARD, CTA2>(d, r_desc, g_desc, idesc, accum);
+#pragma unroll 4
+      for (int k = 1; k < ksteps; ++k)
+        wg_mma<UMMA_A_DISCARD, CTA2>(d, r_desc + (uint64_t)k * 128, g_desc + (uint64_t)k * 128, idesc, 1u);
+    }
+    if (BIAS) {
+      wg_mma<UMMA_A_DISCARD, CTA2>(tmem_base + kWgBiasCol, r_desc, ones_desc, idesc_bias, accum);
+#pragma unroll 4
+      for (int k = 1; k < ksteps; ++k)
+        wg_mma<UMMA_A_DISCARD, CTA2>(tmem_base + kWgBiasCol, r_desc + (uint64_t)k * 128, ones_desc, idesc_bias, 1u);
+    }
+  }
 }
 
 // CTA2 is a template parameter: a kernel that contains cta_group::2 instructions can only be launched as a cluster.
@@ -162,7 +222,9 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
       tma_prefetch_desc(&maps.r);
       int stage = 0;
       uint32_t phase = 0;
-      const int r_loads = a.paired ? 2 : a.r_blocks;
+      // paired: ONE copy of the dz tile, stored one row down; the second M half is the same buffer read one row later
+      // (descriptor LBO = 128 B), not a second TMA copy: 27 % fewer bytes L2 -> SMEM per stage (the kernel is L2-fed)
+      const int r_loads = a.paired ? 1 : a.r_blocks;
       for (int item = item0; item < total_items; item += item_step) {
           const WgItem w = decode_item(a, item, rank);
           // gathered-operand source of this N block
@@ -185,15 +247,15 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
               if (CTA2) tma_load_4d_2cta(m, &full[stage], dst, c0, c1, c2, c3);
               else tma_load_4d(m, &full[stage], dst, c0, c1, c2, c3);
             };
-            // R tile: one TMA per tile row so that rows land with pitch P (halo columns stay zero).  Paired mode:
-            // block 0 holds the tile one row later (row q+1 = pixel q), block 1 holds it in place.
+            // R tile: one TMA per tile row so that rows land with pitch P (halo columns stay zero).  Paired mode: the
+            // tile is stored one row later (row q+1 = pixel q); M half 0 reads it from row 0, M half 1 from row 1.
             for (int rb = 0; rb < r_loads; ++rb) {
               const int ch = a.paired ? w.mb * 128 : w.mb * 128 + rb * 64;
               const int row_off = (a.paired && rb == 0) ? 1 : 0;
               for (int ty = 0; ty < a.TH; ++ty)
                 load(&maps.r, st + rb * a.r_blk_bytes + (uint32_t)(ty * a.P + row_off) * 128, ch, x0, y0 + ty, n);
             }
-            uint8_t* gt = st + 2 * a.r_blk_bytes;
+            uint8_t* gt = st + a.r_region_bytes;
             // gathered operand: this CTA's 64-channel sub-tiles (cta2: sub-tile `rank` of the two)
             if (a.mode == 0) {
               for (int h = 0; h < g_sub; ++h)
@@ -216,7 +278,8 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
     const int mma_n = a.paired ? 192 : a.nbw;                        // paired: three row-shifted views of the x tile
     const uint32_t idesc = umma_idesc_bf16(128 * cl, mma_n, 1, 1);   // both operands MN-major
     const uint32_t idesc_bias = umma_idesc_bf16(128 * cl, 16, 1, 1);
-    const uint64_t hi_r = umma_desc_hi_sw128(a.r_blk_bytes, 1024);
+    // paired: the second 64-lane half of M starts one 128-byte row after the first, inside the same buffer
+    const uint64_t hi_r = umma_desc_hi_sw128(a.paired ? 128u : a.r_blk_bytes, 1024);
     // LBO = distance of the next 64-channel group: the second sub-tile, or (paired) the same tile one image row later
     const uint64_t hi_g = umma_desc_hi_sw128(a.paired ? (uint32_t)a.P * 128u : a.g_tile_bytes, 1024);
     const uint64_t ones_desc = umma_desc(umma_desc_hi_sw128(a.r_blk_bytes, 1024), smem_u32(ones));
@@ -225,8 +288,9 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
     int it = 0;
     const int ksteps = a.kt_rows / 16;
     const int nbw = mma_n;
-    const uint32_t stage_bytes = a.stage_bytes, r_blk_bytes = a.r_blk_bytes;
+    const uint32_t stage_bytes = a.stage_bytes, r_region_bytes = a.r_region_bytes;
     const int n_stages = a.stages;
+    const bool coll_on = a.collector != 0;
     // cta2: the leader issues for the pair; the peer's warp only took part in the TMEM allocation
     for (int item = (CTA2 && rank != 0) ? total_items : item0; item < total_items; item += item_step, ++it) {
         const WgItem w = decode_item(a, item, rank);
@@ -251,6 +315,7 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
           goff[j] = o;
         }
         const int ntap = w.ntap;
+        const int issue_variant = ntap * 2 + (do_bias ? 1 : 0);
         mbar_wait(t_empty, (it & 1) ^ 1);
         tc_fence_after_sync();
         uint32_t accum = 0;
@@ -259,47 +324,16 @@ wgrad_umma_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ W
           tc_fence_after_sync();
           const uint32_t r_base = smem_u32(smem + stage * stage_bytes);
           const uint64_t r_desc = umma_desc(hi_r, r_base);
-          const uint64_t g_desc0 = umma_desc(hi_g, r_base + 2 * r_blk_bytes);
+          const uint64_t g_desc0 = umma_desc(hi_g, r_base + r_region_bytes);
           if (elect_one()) {
-            if (CTA2) {
-#pragma unroll
-              for (int j = 0; j < 6; ++j) {
-                if (j < ntap) {
-                  const uint64_t g_desc = g_desc0 + goff[j];
-                  const uint32_t d = tmem_base + j * nbw;
-                  umma_bf16_2cta(d, r_desc, g_desc, idesc, accum);
-#pragma unroll 4
-                  for (int k = 1; k < ksteps; ++k)
-                    umma_bf16_2cta(d, r_desc + (uint64_t)k * 128, g_desc + (uint64_t)k * 128, idesc, 1u);
-                }
-              }
-              if (do_bias) {
-                umma_bf16_2cta(tmem_base + kWgBiasCol, r_desc, ones_desc, idesc_bias, accum);
-#pragma unroll 4
-                for (int k = 1; k < ksteps; ++k)
-                  umma_bf16_2cta(tmem_base + kWgBiasCol, r_desc + (uint64_t)k * 128, ones_desc, idesc_bias, 1u);
-              }
-              umma_commit_2cta(&empty[stage], (uint16_t)0x3);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 6; ++j) {
-                if (j < ntap) {
-                  const uint64_t g_desc = g_desc0 + goff[j];
-                  const uint32_t d = tmem_base + j * nbw;
-                  // one K step = 16 pixel rows = 2048 B = 128 in the descriptor's (address >> 4) field
-                  umma_bf16(d, r_desc, g_desc, idesc, accum);
-#pragma unroll 4
-                  for (int k = 1; k < ksteps; ++k) umma_bf16(d, r_desc + (uint64_t)k * 128, g_desc + (uint64_t)k * 128, idesc, 1u);
-                }
-              }
-              if (do_bias) {
-                umma_bf16(tmem_base + kWgBiasCol, r_desc, ones_desc, idesc_bias, accum);
-#pragma unroll 4
-                for (int k = 1; k < ksteps; ++k)
-                  umma_bf16(tmem_base + kWgBiasCol, r_desc + (uint64_t)k * 128, ones_desc, idesc_bias, 1u);
-              }
-              umma_commit(&empty[stage]);
+            switch (issue_variant) {
+#define B200_WG_CASE(NT, BIAS) case NT * 2 + BIAS: wg_issue_tile<NT, BIAS, CTA2>(tmem_base, nbw, r_desc, g_desc0, goff, ones_desc, idesc, idesc_bias, ksteps, accum, coll_on); break;
+              B200_WG_CASE(1, 0) B200_WG_CASE(1, 1) B200_WG_CASE(2, 0) B200_WG_CASE(2, 1) B200_WG_CASE(3, 0) B200_WG_CASE(3, 1)
+              B200_WG_CASE(4, 0) B200_WG_CASE(4, 1) B200_WG_CASE(5, 0) B200_WG_CASE(5, 1) B200_WG_CASE(6, 0) B200_WG_CASE(6, 1)
+#undef B200_WG_CASE
+              default: break;
             }
+            if (CTA2) umma_commit_2cta(&empty[stage], (uint16_t)0x3); else umma_commit(&empty[stage]);
           }
           __syncwarp();
           accum = 1;
@@ -448,6 +482,7 @@ wgrad_umma_reduce_kernel(const float* __restrict__ ws, int splits, int taps, int
 static int g_wgrad_n128 = getenv("B200UNET_WGRAD_N64") ? 0 : 1;
 static int g_wgrad_min_stages = getenv("B200UNET_WGRAD_MIN_STAGES") ? atoi(getenv("B200UNET_WGRAD_MIN_STAGES")) : 2;
 static int g_wgrad_cta2 = getenv("B200UNET_WGRAD_NO_PAIRS") ? 0 : 1;
+static int g_wgrad_collector = getenv("B200UNET_WGRAD_NO_COLLECTOR") ? 0 : 1;
 // cost-model cycles per TMA instruction of a stage (the row operand arrives one tile row per instruction): measured on
 // the whole training step 0 -> 31.1 ms, 30 -> 30.7, 70 -> 30.2, 100/150 -> +0.3; without it the planner picked 13 x 19
 // pixel tiles for the first layer (19 tiny row loads per stage) and 0.46 ms where 114 x 2 tiles take 0.38
@@ -510,9 +545,13 @@ static bool wg_make_plan(int mode, int Ho, int Wo, int n_img, int m_total, int n
   // CTA pairs (cta_group::2): two M blocks per work item, each CTA loads one of the two 64-channel gathered sub-tiles
   a.cta2 = (g_wgrad_cta2 && a.nbw == 128 && !a.paired && a.m_blks % 2 == 0 && m_total % 128 == 0) ? 1 : 0;
   a.m_units = a.cta2 ? a.m_blks / 2 : a.m_blks;
+  // A-collector reuse across the taps of a K step: measured (B200, batch 32) 0.51 -> 0.40 ms on the 64-wide N blocks with 4-5
+  // taps per group, 0.85 -> 0.83 ms in paired mode, 1-3 % SLOWER with N = 128 blocks (there the tap-outermost order, whose
+  // consecutive MMAs accumulate into the same TMEM block, wins)
+  a.collector = (g_wgrad_collector && a.nbw == 64) ? 1 : 0;
   const int cl = a.cta2 ? 2 : 1;
   const int g_tiles = (mode == 1 ? taps : 1) * (a.nbw / 64) / cl;  // gathered sub-tiles per CTA and stage
-  const int r_loads = a.paired ? 2 : a.r_blocks;
+  const int r_loads = a.paired ? 1 : a.r_blocks;
   const double mma_groups = a.paired ? 2.0 : (taps == 9 ? (a.nbw == 128 ? 3.0 : 4.5) : (double)taps);
   const double mma_cycles = a.paired ? 96.0 : (a.nbw == 128 ? 64.0 : 48.0);
   const double passes = a.tap_groups;
@@ -528,7 +567,8 @@ static bool wg_make_plan(int mode, int Ho, int Wo, int n_img, int m_total, int n
       const uint32_t r_blk = (uint32_t)kt * 128;
       const uint32_t g_rows = (uint32_t)max((TH + a.halo) * P, kt + a.halo * P + a.halo);
       const uint32_t g_tile = (g_rows * 128 + 1023) & ~1023u;
-      const uint32_t stage = 2 * r_blk + g_tiles * g_tile;
+      const uint32_t r_region = a.paired ? r_blk + 1024 : 2 * r_blk;  // paired: rows 0 .. kt (the second M half starts at row 1)
+      const uint32_t stage = r_region + g_tiles * g_tile;
       if ((uint32_t)g_wgrad_min_stages * stage + kWgOnesBytes + 1024 > kWgSmemBudget) continue;  // >= 3 stages: fed from L2, latency must hide
       const long long tiles = (long long)((Wo + TW - 1) / TW) * ((Ho + TH - 1) / TH) * n_img;
       // per tile and pass: MMA time ~ MMA groups * K steps * ~48 cycles (shared-memory-bound N = 64 MMA), load time ~
@@ -545,6 +585,7 @@ static bool wg_make_plan(int mode, int Ho, int Wo, int n_img, int m_total, int n
         a.TH = TH;
         a.TW = TW;
         a.r_blk_bytes = r_blk;
+        a.r_region_bytes = r_region;
         a.g_tile_bytes = g_tile;
         a.g_box_bytes = (uint32_t)(TH + a.halo) * P * 128;
         a.stage_bytes = stage;
