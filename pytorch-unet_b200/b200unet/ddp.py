@@ -39,6 +39,10 @@ class GradBucketer:
         assert grad_dtype in ("fp32", "bf16")
         self.grad_dtype = grad_dtype  # wire precision of the all-reduce (the arena and the optimizer stay fp32)
         self.profile = False          # bench.py: measure how long the end of backward waits for the collectives
+        # deferred mode (b200unet.GraphedTrainStep): backward only fills the arena; the caller reduces it in ONE collective
+        # between two CUDA graphs (a NCCL call issued from inside a stream capture deadlocked with the async bucket logic)
+        self.defer = False
+        self.deferred_arena: Optional[torch.Tensor] = None
         self._prof: List[Tuple[torch.cuda.Event, torch.cuda.Event]] = []
         self.names = list(names)
         self.shapes = dict(shapes)
@@ -90,7 +94,7 @@ class GradBucketer:
             self._reduce(b)
 
     def _reduce(self, b: int) -> None:
-        if self.world <= 1:
+        if self.world <= 1 or self.defer:
             return
         s, e, _ = self.buckets[b]
         buf = self.arena[s:e]
@@ -106,7 +110,21 @@ class GradBucketer:
             h = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
             self._handles.append((h, buf if self.average else None, None))
 
+    def reduce_all(self, arena: torch.Tensor) -> None:
+        """One blocking-on-stream all-reduce (average) of a whole arena: the collective of the graphed step."""
+        if self.world <= 1:
+            return
+        if self._nccl and self.average:
+            dist.all_reduce(arena, op=dist.ReduceOp.AVG, group=self.pg)
+        else:
+            dist.all_reduce(arena, op=dist.ReduceOp.SUM, group=self.pg)
+            if self.average:
+                arena.div_(self.world)
+
     def finish(self) -> None:
+        if self.defer:
+            self.deferred_arena, self.arena, self._handles = self.arena, None, []
+            return
         prof = self.profile and self._handles and self.arena is not None and self.arena.is_cuda \
             and not torch.cuda.is_current_stream_capturing()
         if prof:

@@ -7,6 +7,8 @@
 //   forward : thread = 4 consecutive pixels x 16 output channels (64 accumulators, 16 FMAs per LDS.128 of weights)
 //   wgrad   : thread = CPT output channels x all 9*Cin taps, grid-strided over pixels; warp-shuffle + shared-memory
 //             block reduction, per-block partials, fixed-order final reduction (reproducible); bias gradient for free
+#include <cstdlib>
+
 #include "conv_impl.h"
 #include "ptx.cuh"
 
@@ -180,6 +182,165 @@ smallc_fwd_kernel(DView src, DView dst, const float* __restrict__ w, const float
       }
     }
     if (more) park(buf ^ 1);  // the other slab was last read one iteration ago, before the __syncwarp below
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------ forward on the tensor cores (bf16 tier)
+// The CUDA-core kernel above stays issue-/latency-bound at ~22 TFLOP/s (ncu: FMA pipe 42 % busy, issue 42 %: 576 * CIN FMAs per
+// pixel are simply too many instructions for a layer that should cost one write of the 64-channel tensor).  Here the
+// 9 * CIN patch values of a pixel are the K dimension of a warp-level mma.sync.m16n8k16 (bf16 x bf16 -> fp32): K = 16 per
+// step holds the whole 3x3 patch of one input channel pair, the weight fragments of all 64 output channels stay in
+// registers for the whole kernel, and a warp turns 32 pixels x 64 channels into 16 * ceil(9 CIN / 16) tensor instructions
+// instead of 9216 * CIN / 32 FMAs per lane.  (tcgen05 would need the patches in shared memory in UMMA layout and a TMEM
+// round trip for a GEMM with K = 16: legacy mma.sync from registers is the right tool for this one layer.)
+//   A (16 pixels x 16 k): built from the warp's staged bf16 window with two LDS.U16 per register — lane (g, t) needs
+//     pixels g / g + 8 and k = 2t, 2t+1, 2t+8, 2t+9, whose window offsets are per-lane constants;
+//   B (16 k x 8 channels) = w[o][k] (k = c * 9 + tap is contiguous in the OIHW tensor), bf16-rounded like every other
+//     layer's weights;
+//   C starts from the bias; ReLU is the .relu of the bf16x2 conversion; the 16 x 64 result goes through a padded
+//     warp-private shared-memory tile so that 8 lanes store one pixel's 128 contiguous bytes.
+constexpr int kMmaPitch = 40;                 // bf16 per staged window row: 34 used
+constexpr int kMmaStageRow = 72;              // 32-bit words per staged output row: 64 used (+8: conflict-free column writes)
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int CIN>
+__global__ void __launch_bounds__(kScThreads, 2)
+smallc_mma_fwd_kernel(DView src, DView dst, const float* __restrict__ w, const float* __restrict__ bias, int relu, int pad) {
+  constexpr int KR = 9 * CIN;            // real K
+  constexpr int KS = (KR + 15) / 16;     // K steps
+  constexpr int WROWS = 3 * CIN + 1;     // staged window rows (+1: a row of zeros for the padding k)
+  __shared__ __align__(16) unsigned short xs[kScThreads / 32][2][WROWS][kMmaPitch];
+  __shared__ __align__(16) uint32_t stg[kScThreads / 32][16][kMmaStageRow / 2];  // bf16x2 words: 16 pixels x 64 channels
+  const int cout = dst.c;
+  const int o_base = blockIdx.y * 64;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+
+  // weight fragments: b[ks][j][0] = {W[k0][o], W[k0+1][o]}, b[ks][j][1] = {W[k0+8][o], W[k0+9][o]}, k0 = 16 ks + 2t, o = o_base + 8j + g
+  uint32_t bw[KS][8][2];
+  float bz[8][2];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int o = o_base + j * 8 + g;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k0 = ks * 16 + 2 * t + 8 * h;
+        const float w0 = (o < cout && k0 < KR) ? w[(long long)o * KR + k0] : 0.f;
+        const float w1 = (o < cout && k0 + 1 < KR) ? w[(long long)o * KR + k0 + 1] : 0.f;
+        bw[ks][j][h] = pack_bf16x2(w0, w1);
+      }
+    const int oc = o_base + j * 8 + 2 * t;  // the accumulator columns of this lane
+    bz[j][0] = (bias && oc < cout) ? bias[oc] : 0.f;
+    bz[j][1] = (bias && oc + 1 < cout) ? bias[oc + 1] : 0.f;
+  }
+  // window offsets of this lane's k values: k = c * 9 + r * 3 + s lives at row r * CIN + c, column + s; padding k -> zero row
+  int koff[KS][4];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = ks * 16 + 2 * t + (q & 1) + 8 * (q >> 1);
+      const int c = k / 9, tap = k - c * 9, r = tap / 3, sx = tap - r * 3;
+      koff[ks][q] = k < KR ? (r * CIN + c) * kMmaPitch + sx : (3 * CIN) * kMmaPitch;
+    }
+  for (int i = lane; i < 2 * kMmaPitch; i += 32) xs[warp][i / kMmaPitch][3 * CIN][i % kMmaPitch] = 0;  // the zero rows
+
+  const unsigned segs = (unsigned)(dst.w + 31) / 32;
+  const unsigned total = (unsigned)dst.n * dst.h * segs;
+  const unsigned step = gridDim.x * (kScThreads / 32);
+  unsigned short v[3 * CIN][2];
+  auto fetch = [&](unsigned unit) {
+    const unsigned seg = unit % segs, tt = unit / segs;
+    const int oy = (int)(tt % dst.h), n = (int)(tt / dst.h);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int iy = oy + r - pad;
+      const bool yok = iy >= 0 && iy < src.h;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int ix = (int)seg * 32 + lane + 32 * e - pad;
+        const bool ok = yok && ix >= 0 && ix < src.w && (e == 0 || lane < 2);
+        const long long so = ok ? src.off(n, iy, ix) : 0;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c)
+          v[r * CIN + c][e] = ok ? reinterpret_cast<const unsigned short*>(src.p)[so + c] : (unsigned short)0;
+      }
+    }
+  };
+  auto park = [&](int buf) {
+#pragma unroll
+    for (int rc = 0; rc < 3 * CIN; ++rc) {
+      xs[warp][buf][rc][lane] = v[rc][0];
+      if (lane < 2) xs[warp][buf][rc][32 + lane] = v[rc][1];
+    }
+  };
+
+  unsigned unit = blockIdx.x * (kScThreads / 32) + warp;
+  int buf = 0;
+  if (unit < total) {
+    fetch(unit);
+    park(0);
+  }
+  __syncwarp();
+  for (; unit < total; unit += step, buf ^= 1) {
+    const bool more = unit + step < total;
+    if (more) fetch(unit + step);  // in flight during the tensor instructions below
+    const unsigned seg = unit % segs, tt = unit / segs;
+    const int oy = (int)(tt % dst.h), n = (int)(tt / dst.h);
+    const unsigned short* win = &xs[warp][buf][0][0];
+#pragma unroll 1
+    for (int mt = 0; mt < 2; ++mt) {  // two tiles of 16 pixels
+      const int px0 = (int)seg * 32 + mt * 16;
+      if (px0 >= dst.w) break;
+      float acc[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[j][0] = bz[j][0];
+        acc[j][1] = bz[j][1];
+        acc[j][2] = bz[j][0];
+        acc[j][3] = bz[j][1];
+      }
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t a[4];
+        const unsigned short* wp = win + mt * 16 + g;
+        a[0] = (uint32_t)wp[koff[ks][0]] | ((uint32_t)wp[koff[ks][1]] << 16);          // pixel g,     k = 2t, 2t + 1
+        a[1] = (uint32_t)wp[koff[ks][0] + 8] | ((uint32_t)wp[koff[ks][1] + 8] << 16);  // pixel g + 8
+        a[2] = (uint32_t)wp[koff[ks][2]] | ((uint32_t)wp[koff[ks][3]] << 16);          // pixel g,     k = 2t + 8, 2t + 9
+        a[3] = (uint32_t)wp[koff[ks][2] + 8] | ((uint32_t)wp[koff[ks][3] + 8] << 16);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mma_bf16_16816(acc[j], a, bw[ks][j]);
+      }
+      // lane (g, t) holds pixels g / g + 8, channels 8j + 2t, 8j + 2t + 1: park as bf16x2 words, row pitch 36 words
+      // (word index 36 row + 4j + t: the 32 lanes of one store hit 32 different banks)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        stg[warp][g][j * 4 + t] = relu ? pack_bf16x2_relu(acc[j][0], acc[j][1]) : pack_bf16x2(acc[j][0], acc[j][1]);
+        stg[warp][g + 8][j * 4 + t] = relu ? pack_bf16x2_relu(acc[j][2], acc[j][3]) : pack_bf16x2(acc[j][2], acc[j][3]);
+      }
+      __syncwarp();
+      // 8 lanes move one pixel's 128 bytes: lane -> (pixel lane / 8 + 4 i, 16-byte chunk lane % 8)
+      const int ch = lane & 7;
+      if (o_base + ch * 8 < cout) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int pr = (lane >> 3) + 4 * i;
+          const int ox = px0 + pr;
+          if (ox < dst.w)
+            *reinterpret_cast<uint4*>(dst.p + dst.off(n, oy, ox) + o_base + ch * 8) =
+                *reinterpret_cast<const uint4*>(&stg[warp][pr][ch * 4]);
+        }
+      }
+      __syncwarp();
+    }
+    if (more) park(buf ^ 1);  // the other window was last read one iteration ago
     __syncwarp();
   }
 }
@@ -360,7 +521,28 @@ static int sc_fwd_launch(const b200_conv_fwd_params* p, cudaStream_t st) {
   return check_launch("smallc_fwd");
 }
 
+template <int CIN>
+static int sc_mma_fwd_launch(const b200_conv_fwd_params* p, cudaStream_t st) {
+  const long long units = (long long)p->dst.n * p->dst.h * ((p->dst.w + 31) / 32);
+  if (units >= (1LL << 32)) return fail(-1, "smallc_fwd: more than 2^32 row segments");
+  long long gx = (units + kScThreads / 32 - 1) / (kScThreads / 32);
+  if (gx > 2 * kNumSMsB200) gx = 2 * kNumSMsB200;
+  dim3 grid((unsigned)gx, (unsigned)((p->dst.c + 63) / 64));
+  smallc_mma_fwd_kernel<CIN><<<grid, kScThreads, 0, st>>>(dview(p->src[0]), dview(p->dst), p->w_f32, p->bias, p->relu, p->pad);
+  return check_launch("smallc_fwd (mma)");
+}
+
+static int g_sc_mma = getenv("B200UNET_NO_FIRST_LAYER_MMA") ? 0 : 1;
+
 int smallc_conv_fwd(const b200_conv_fwd_params* p, cudaStream_t st) {
+  if (g_sc_mma && !p->src[0].lo && !p->dst.lo) {  // bf16 tier: tensor-core kernel; the split tier keeps fp32 weights / CUDA cores
+    switch (p->src[0].c) {
+      case 1: return sc_mma_fwd_launch<1>(p, st);
+      case 2: return sc_mma_fwd_launch<2>(p, st);
+      case 3: return sc_mma_fwd_launch<3>(p, st);
+      default: return sc_mma_fwd_launch<4>(p, st);
+    }
+  }
   switch (p->src[0].c) {
     case 1: return sc_fwd_launch<1>(p, st);
     case 2: return sc_fwd_launch<2>(p, st);

@@ -94,3 +94,55 @@ def test_two_ranks_one_gpu_gloo_equal_single_process(tmp_path):
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_two_ranks_nccl_equal_single_process(tmp_path):
     _run("nccl", tmp_path)
+
+
+def _graph_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    import b200unet
+    from b200unet.ddp import DataParallel
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    x, y = _data()
+    xs, ys = x[rank * B:(rank + 1) * B].to(dev), y[rank * B:(rank + 1) * B].to(dev)
+    out = {}
+    for mode in ("eager", "graph"):
+        torch.manual_seed(7)
+        model = b200unet.UNet(*ARGS).to(dev).train()
+        net = DataParallel(model, bucket_bytes=256 << 10)
+        opt = b200unet.FusedAdam(model.parameters(), lr=1e-3)
+        if mode == "graph":
+            step = b200unet.GraphedTrainStep(net, opt, xs, ys, warmup=1)   # 1 warm-up step + 1 capture-time reduce
+            losses = [float(step(xs, ys)) for _ in range(3)]
+        else:
+            losses = []
+            for _ in range(4):                                             # the same number of optimizer updates
+                loss = net.loss(xs, ys)
+                opt.zero_grad(set_to_none=True)
+                loss.backward()
+                opt.step()
+                losses.append(float(loss))
+        torch.cuda.synchronize()
+        out[mode] = {"w": {k: p.detach().cpu() for k, p in model.named_parameters()}, "loss": losses[-1]}
+    torch.save(out, os.path.join(out_dir, f"graph_rank{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_graphed_step_with_data_parallel_two_ranks(tmp_path):
+    """GraphedTrainStep over DataParallel = graph(fwd + bwd) -> one all-reduce of the gradient arena -> graph(optimizer):
+    after the same number of updates the weights equal the eager bucketed data-parallel run, on both ranks."""
+    import torch.multiprocessing as mp
+    from gpu_util import rel_l2
+    mp.spawn(_graph_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    r0 = torch.load(os.path.join(tmp_path, "graph_rank0.pt"))
+    r1 = torch.load(os.path.join(tmp_path, "graph_rank1.pt"))
+    for k in r0["graph"]["w"]:
+        assert torch.equal(r0["graph"]["w"][k], r1["graph"]["w"][k]), f"replicas differ in {k}"
+    keys = list(r0["graph"]["w"])
+    got = torch.cat([r0["graph"]["w"][k].flatten() for k in keys])
+    want = torch.cat([r0["eager"]["w"][k].flatten() for k in keys])
+    assert rel_l2(got, want) < 1e-5
+    assert abs(r0["graph"]["loss"] - r0["eager"]["loss"]) < 1e-4
