@@ -15,7 +15,7 @@ def header_symbols():
 def test_library_exports_header_symbols(lib_built):
     lib = ctypes.CDLL(lib_built)
     syms = header_symbols()
-    assert len(syms) >= 35
+    assert len(syms) >= 50
     for s in syms:
         assert hasattr(lib, s), s
 
@@ -33,6 +33,16 @@ def test_sass_is_sm100a(lib_built):
     import subprocess
     out = subprocess.run(["cuobjdump", "-lelf", lib_built], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+
+
+def test_sass_contains_tcgen05_tmem_and_tma(lib_built):
+    """The hot path is tensor-memory code, not a CUDA-core fallback: tcgen05.mma (UTCHMMA, single-CTA and .2CTA), TMA
+    loads (UTMALDG), TMEM loads / stores (LDTM / STTM) and tcgen05.commit (UTCBAR) are present in the built library."""
+    import subprocess
+    sass = subprocess.run(["cuobjdump", "-sass", lib_built], capture_output=True, text=True).stdout
+    for mnemonic, at_least in [("UTCHMMA", 100), ("UTCHMMA.2CTA", 50), ("UTMALDG", 40), ("LDTM", 10), ("STTM", 10),
+                               ("UTCBAR", 40)]:
+        assert sass.count(mnemonic) >= at_least, (mnemonic, sass.count(mnemonic))
 
 
 def test_bad_arguments_are_reported_not_crashed(lib_built):
