@@ -149,6 +149,9 @@ int b200unet_device_ok(void);
 int b200unet_num_sms(void);
 /* number of kernel launches this library has made in this process (for bench.py's gpu_launches) */
 unsigned long long b200unet_launch_count(void);
+/* convolution calls that B200_IMPL_AUTO had to route to the CUDA-core fallback although they have more than 7 channels
+ * (a 10-50x performance cliff; also reported once per entry point on stderr unless B200UNET_QUIET is set) */
+unsigned long long b200unet_fallback_count(void);
 
 int b200unet_conv_fwd(const b200_conv_fwd_params* p, void* stream);
 int b200unet_conv_dgrad(const b200_conv_dgrad_params* p, void* stream);

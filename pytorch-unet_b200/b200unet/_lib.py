@@ -82,6 +82,7 @@ SIGNATURES = {
     "b200unet_device_ok": (_I, []),
     "b200unet_num_sms": (_I, []),
     "b200unet_launch_count": (C.c_ulonglong, []),
+    "b200unet_fallback_count": (C.c_ulonglong, []),
     "b200unet_conv_fwd": (_I, [C.POINTER(ConvFwdParams), _P]),
     "b200unet_conv_dgrad": (_I, [C.POINTER(ConvDgradParams), _P]),
     "b200unet_conv_wgrad_workspace_bytes": (_SZ, [C.POINTER(ConvWgradParams)]),

@@ -1,5 +1,9 @@
 // C-ABI entry points of the convolution family: argument validation and the choice between the tcgen05 kernels
 // and the CUDA-core kernels (B200_IMPL_AUTO picks tcgen05 whenever the shape allows it).
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+
 #include "conv_impl.h"
 
 using namespace b200;
@@ -62,6 +66,25 @@ int cin_of(const b200_conv_wgrad_params* p) {
   return c;
 }
 
+// B200_IMPL_AUTO silently dropping from the tcgen05 kernels to the CUDA-core `direct` ones is a 10-50x performance cliff
+// (channel counts that are not multiples of 8, misaligned views).  Small channel counts (<= 7: the image side of the
+// first layer) are served by design; anything wider is counted and reported once per entry point on stderr
+// (B200UNET_QUIET=1 silences it; b200unet_fallback_count() lets a host binding surface it).
+std::atomic<unsigned long long> g_fallbacks{0};
+void note_fallback(const char* what, int channels) {
+  if (channels <= 7) return;
+  g_fallbacks.fetch_add(1);
+  static std::atomic<unsigned> warned{0};
+  static const bool quiet = getenv("B200UNET_QUIET") != nullptr;
+  unsigned bit = 1u;
+  for (const char* c = what; *c; ++c) bit = bit * 31u + (unsigned)*c;
+  bit = 1u << (bit % 32u);
+  if (!quiet && !(warned.fetch_or(bit) & bit))
+    fprintf(stderr, "[b200unet] %s with %d channels does not qualify for the tcgen05 kernel (channel counts must be multiples of 8, "
+            "views 16-byte aligned): running the CUDA-core fallback, expect 10-50x lower throughput.  Pad the channels "
+            "(b200unet.UNet does this itself) or set B200UNET_QUIET=1.\n", what, channels);
+}
+
 template <class P, class OkFn>
 int resolve(const P* p, OkFn ok, const char* what, int* impl) {
   *impl = p->impl;
@@ -74,6 +97,8 @@ int resolve(const P* p, OkFn ok, const char* what, int* impl) {
 }  // namespace
 
 extern "C" {
+
+unsigned long long b200unet_fallback_count(void) { return g_fallbacks.load(); }
 
 int b200unet_conv_fwd_impl(const b200_conv_fwd_params* p) {
   if (check_conv_fwd(p)) return -1;
@@ -107,6 +132,7 @@ int b200unet_conv_fwd(const b200_conv_fwd_params* p, void* stream) {
   if ((r = resolve(p, umma_conv_fwd_ok, "conv_fwd", &impl))) return r;
   if (impl == B200_IMPL_UMMA) return umma_conv_fwd(p, as_stream(stream));
   if (p->impl == B200_IMPL_AUTO && smallc_conv_fwd_ok(p)) return smallc_conv_fwd(p, as_stream(stream));
+  if (p->impl == B200_IMPL_AUTO) note_fallback("conv_fwd", p->src[0].c);
   B200_REQUIRE(!p->dst.lo, "conv_fwd: the split precision tier runs on the tcgen05 / first-layer kernels only");
   return direct_conv_fwd(p, as_stream(stream));
 }
@@ -115,6 +141,7 @@ int b200unet_conv_dgrad(const b200_conv_dgrad_params* p, void* stream) {
   int r = check_conv_dgrad(p), impl;
   if (r) return r;
   if ((r = resolve(p, umma_conv_dgrad_ok, "conv_dgrad", &impl))) return r;
+  if (impl == B200_IMPL_DIRECT && p->impl == B200_IMPL_AUTO) note_fallback("conv_dgrad", p->dst[0].c);
   return impl == B200_IMPL_UMMA ? umma_conv_dgrad(p, as_stream(stream)) : direct_conv_dgrad(p, as_stream(stream));
 }
 
