@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define B200UNET_ABI_VERSION 3
+#define B200UNET_ABI_VERSION 4
 
 /* Strided NHWC view of a bf16 tensor.  Channel stride is 1.  Strides in elements.
  *
@@ -197,6 +197,12 @@ int b200unet_maxpool2x2_fwd(const b200_view* x, const b200_view* y, uint8_t* idx
  * mask: optional bf16 laid out like dx.                                                                    */
 int b200unet_maxpool2x2_bwd(const b200_view* dy, const uint8_t* idx8, const b200_view* dx, const b200_view* add,
                             int add_y, int add_x, const void* mask, void* stream);
+/* Same result with 30-35 % fewer bytes when the producer's ReLU mask is the POOLED tensor's own source (no BatchNorm): the
+ * scattered term is masked by [y_pooled > 0] (y_pooled = the forward output of the pool, laid out like dy: the arg-max
+ * position holds exactly that value) and `add` must arrive ALREADY masked (conv_dgrad's mask[] of that destination), so the
+ * full-resolution mask is never read.  Bit-identical to b200unet_maxpool2x2_bwd(..., mask).                             */
+int b200unet_maxpool2x2_bwd_premasked(const b200_view* dy, const uint8_t* idx8, const b200_view* y_pooled, const b200_view* dx,
+                                      const b200_view* add, int add_y, int add_x, void* stream);
 
 /* ---- nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False); mask optional, laid out like dx */
 int b200unet_bilinear_up2x_fwd(const b200_view* x, const b200_view* y, void* stream);

@@ -103,6 +103,7 @@ SIGNATURES = {
     "b200unet_pack_convt_weight": (_I, [_P, _I, _I, _I, _P, _P]),
     "b200unet_maxpool2x2_fwd": (_I, [_VP, _VP, _P, _P, _P]),
     "b200unet_maxpool2x2_bwd": (_I, [_VP, _P, _VP, _VP, _I, _I, _P, _P]),
+    "b200unet_maxpool2x2_bwd_premasked": (_I, [_VP, _P, _VP, _VP, _VP, _I, _I, _P]),
     "b200unet_bilinear_up2x_fwd": (_I, [_VP, _VP, _P]),
     "b200unet_bilinear_up2x_bwd": (_I, [_VP, _VP, _P, _P]),
     "b200unet_bn_workspace_bytes": (_SZ, [_I]),
@@ -151,7 +152,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.b200unet_abi_version() != 3:
+    if lib.b200unet_abi_version() != 4:
         raise RuntimeError("libb200unet.so ABI version mismatch: rebuild with pytorch-unet_b200/build.py")
     _lib = lib
     return lib

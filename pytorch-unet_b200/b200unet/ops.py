@@ -265,9 +265,19 @@ def maxpool_fwd(x: torch.Tensor, want_idx64: bool = False):
 
 
 def maxpool_bwd(dy: torch.Tensor, idx8: torch.Tensor, dx: torch.Tensor, add: Optional[torch.Tensor] = None,
-                add_y: int = 0, add_x: int = 0, mask: Optional[torch.Tensor] = None) -> None:
+                add_y: int = 0, add_x: int = 0, mask: Optional[torch.Tensor] = None,
+                pooled: Optional[torch.Tensor] = None) -> None:
+    """pooled (the pool's forward output) selects the pre-masked form: `add` is already ReLU-masked by its producer and
+    the scattered term is masked by [pooled > 0]; `mask` must then be None."""
     vdy, vdx = view(dy), view(dx)
     vadd = view(add) if add is not None else None
+    if pooled is not None:
+        assert mask is None
+        vy = view(hi_of(pooled))
+        check(_lib.load().b200unet_maxpool2x2_bwd_premasked(C.byref(vdy), idx8.data_ptr(), C.byref(vy), C.byref(vdx),
+                                                            C.byref(vadd) if vadd is not None else None, add_y, add_x,
+                                                            stream_ptr()), "maxpool2x2_bwd_premasked")
+        return
     if mask is not None:
         assert mask.stride() == dx.stride() and mask.shape == dx.shape
     check(_lib.load().b200unet_maxpool2x2_bwd(C.byref(vdy), idx8.data_ptr(), C.byref(vdx),

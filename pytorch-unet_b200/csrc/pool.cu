@@ -77,7 +77,10 @@ maxpool_fwd_kernel(DView x, DView y, uint8_t* __restrict__ idx8, long long* __re
 template <int VEC>
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(DView dy, const uint8_t* __restrict__ idx8, DView dx, DView add, int has_add, int add_y, int add_x,
-                   const bf16* __restrict__ mask) {
+                   const bf16* __restrict__ mask, const bf16* __restrict__ ypool) {
+  // ypool (pre-masked mode, laid out like dy): the pooled activation.  The ReLU mask of the scattered term is then
+  // [pooled value > 0] (the arg-max position holds exactly that value) and the skip-gradient window arrives already
+  // masked by the kernel that produced it, so the full-resolution mask tensor is not read at all.
   // one block per window row (n, oh): only 32-bit index arithmetic per element
   const int lanes = dx.c / VEC;
   const int wh = (dx.h + 1) / 2, ww = (dx.w + 1) / 2;
@@ -99,6 +102,12 @@ maxpool_bwd_kernel(DView dy, const uint8_t* __restrict__ idx8, DView dx, DView a
         float t[8];
         unpack8(*reinterpret_cast<const bf16x8*>(s), t);
         const uint2 cw = *reinterpret_cast<const uint2*>(idx8 + opix * dy.c + l * 8);
+        if (ypool) {
+          float yv[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(ypool + dy.off(n, oh, ow) + l * 8), yv);
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) t[j] = yv[j] > 0.f ? t[j] : 0.f;
+        }
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
           g[j] = t[j];
@@ -106,6 +115,7 @@ maxpool_bwd_kernel(DView dy, const uint8_t* __restrict__ idx8, DView dx, DView a
         }
       } else {
         g[0] = bf2f(s[0]);
+        if (ypool && !(bf2f(ypool[dy.off(n, oh, ow) + l]) > 0.f)) g[0] = 0.f;
         code[0] = idx8[opix * dy.c + l];
       }
     }
@@ -184,8 +194,8 @@ int b200unet_maxpool2x2_fwd(const b200_view* x, const b200_view* y, uint8_t* idx
   return check_launch("maxpool_fwd");
 }
 
-int b200unet_maxpool2x2_bwd(const b200_view* dy, const uint8_t* idx8, const b200_view* dx, const b200_view* add,
-                            int add_y, int add_x, const void* mask, void* stream) {
+static int maxpool_bwd_launch(const b200_view* dy, const uint8_t* idx8, const b200_view* dx, const b200_view* add, int add_y,
+                              int add_x, const void* mask, const b200_view* ypool, void* stream) {
   B200_REQUIRE(view_ok(dy) && view_ok(dx) && idx8, "maxpool_bwd: bad arguments");
   B200_REQUIRE(dy->n == dx->n && dy->c == dx->c && dy->h == dx->h / 2 && dy->w == dx->w / 2,
                "maxpool_bwd: dy extent must be floor(dx/2)");
@@ -194,15 +204,33 @@ int b200unet_maxpool2x2_bwd(const b200_view* dy, const uint8_t* idx8, const b200
                      add_y + add->h <= dx->h && add_x + add->w <= dx->w,
                  "maxpool_bwd: skip-gradient window outside dx");
   }
+  if (ypool) {
+    B200_REQUIRE(view_ok(ypool) && same_extent(*ypool, *dy) && ypool->stride_n == dy->stride_n &&
+                     ypool->stride_h == dy->stride_h && ypool->stride_w == dy->stride_w,
+                 "maxpool_bwd: the pooled activation must be laid out like dy");
+  }
   const bool v8 = vec8_ok(*dy) && vec8_ok(*dx) && (!add || vec8_ok(*add)) &&
-                  reinterpret_cast<uintptr_t>(idx8) % 8 == 0 && reinterpret_cast<uintptr_t>(mask) % 16 == 0;
+                  reinterpret_cast<uintptr_t>(idx8) % 8 == 0 && reinterpret_cast<uintptr_t>(mask) % 16 == 0 &&
+                  (!ypool || reinterpret_cast<uintptr_t>(ypool->ptr) % 16 == 0);
   DView dadd = add ? dview(*add) : dview(*dx);
+  const bf16* yp = ypool ? (const bf16*)ypool->ptr : nullptr;
   if (v8)
     maxpool_bwd_kernel<8><<<(unsigned)(dx->n * ((dx->h + 1) / 2)), 256, 0, as_stream(stream)>>>(dview(*dy), idx8, dview(*dx), dadd,
-                                                                            add ? 1 : 0, add_y, add_x, (const bf16*)mask);
+                                                                            add ? 1 : 0, add_y, add_x, (const bf16*)mask, yp);
   else
     maxpool_bwd_kernel<1><<<(unsigned)(dx->n * ((dx->h + 1) / 2)), 256, 0, as_stream(stream)>>>(dview(*dy), idx8, dview(*dx), dadd,
-                                                                            add ? 1 : 0, add_y, add_x, (const bf16*)mask);
+                                                                            add ? 1 : 0, add_y, add_x, (const bf16*)mask, yp);
   return check_launch("maxpool_bwd");
+}
+
+int b200unet_maxpool2x2_bwd(const b200_view* dy, const uint8_t* idx8, const b200_view* dx, const b200_view* add,
+                            int add_y, int add_x, const void* mask, void* stream) {
+  return maxpool_bwd_launch(dy, idx8, dx, add, add_y, add_x, mask, nullptr, stream);
+}
+
+int b200unet_maxpool2x2_bwd_premasked(const b200_view* dy, const uint8_t* idx8, const b200_view* y_pooled, const b200_view* dx,
+                                      const b200_view* add, int add_y, int add_x, void* stream) {
+  B200_REQUIRE(y_pooled, "maxpool_bwd_premasked: the pooled activation is required");
+  return maxpool_bwd_launch(dy, idx8, dx, add, add_y, add_x, nullptr, y_pooled, stream);
 }
 }

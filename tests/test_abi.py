@@ -24,7 +24,7 @@ def test_python_binding_covers_header(lib_built):
     from b200unet import _lib
     assert sorted(_lib.SIGNATURES.keys()) == header_symbols()
     lib = _lib.load()
-    assert lib.b200unet_abi_version() == 3
+    assert lib.b200unet_abi_version() == 4
     assert lib.b200unet_bn_workspace_bytes(64) > 0
     assert lib.b200unet_head_workspace_bytes(64, 2) > 0
 

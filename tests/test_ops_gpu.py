@@ -278,3 +278,27 @@ def test_errors_are_raised(ops):
     with pytest.raises(RuntimeError):
         ops.conv_fwd([x], torch.randn(8, 8, 3, 3, device=dev()), None, 0, True,
                      out=torch.empty(1, 3, 3, 8, dtype=torch.bfloat16, device=dev()))
+
+
+@pytest.mark.parametrize("n,c,h,w,crop", [(2, 64, 12, 20, (2, 4, 6, 10)), (1, 8, 7, 9, (1, 1, 4, 6)), (1, 16, 10, 10, None)])
+def test_maxpool_bwd_premasked_is_bit_identical(ops, n, c, h, w, crop):
+    """b200unet_maxpool2x2_bwd_premasked (skip gradient masked by its producer, scattered term masked by [pooled > 0]) must
+    give exactly the bytes of the masked form that reads the full-resolution ReLU mask."""
+    torch.manual_seed(11)
+    act = torch.relu(torch.randn(n, h, w, c, device="cuda")).to(torch.bfloat16)     # post-ReLU producer output (~half zeros)
+    act[:, :2, :2] = 0                                                               # an all-zero window
+    pooled, idx8 = ops.maxpool_fwd(act)
+    g = torch.randn(n, h // 2, w // 2, c, device="cuda").to(torch.bfloat16)
+    ref = torch.zeros(n, h, w, c, device="cuda", dtype=torch.bfloat16)
+    new = torch.zeros_like(ref)
+    if crop is not None:
+        y0, x0, ch, cw = crop
+        skip = torch.randn(n, ch, cw, c, device="cuda").to(torch.bfloat16)
+        ref[:, y0:y0 + ch, x0:x0 + cw] = skip
+        new[:, y0:y0 + ch, x0:x0 + cw] = torch.where(act[:, y0:y0 + ch, x0:x0 + cw] > 0, skip, torch.zeros_like(skip))
+        ops.maxpool_bwd(g, idx8, ref, add=ref[:, y0:y0 + ch, x0:x0 + cw], add_y=y0, add_x=x0, mask=act)
+        ops.maxpool_bwd(g, idx8, new, add=new[:, y0:y0 + ch, x0:x0 + cw], add_y=y0, add_x=x0, pooled=pooled)
+    else:
+        ops.maxpool_bwd(g, idx8, ref, mask=act)
+        ops.maxpool_bwd(g, idx8, new, pooled=pooled)
+    assert torch.equal(ref.view(torch.int16), new.view(torch.int16))
