@@ -24,5 +24,5 @@ cap() {  # name regex count "launches to stall-report"
 }
 cap conv  '.*umma_conv_kernel.*' 26 "0 1 9 18 20 21 22 23"
 cap wgrad '.*wgrad_umma_kernel.*' 4 "0 1 2"
-cap hbm   '.*(head_dense|head_kernel|smallc_fwd|im2col|maxpool_bwd).*' 5 "0 1 2 3 4"
+cap hbm   ".*(head_pix|smallc_mma|im2col3x3_c1|maxpool_bwd|maxpool_fwd).*" 8 "0 1 2 3 4"
 du -sh $OUT
