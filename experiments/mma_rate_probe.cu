@@ -50,8 +50,8 @@ __global__ void __launch_bounds__(128, 1) probe(P p, long long* out) {
 int main() {
   long long* d; cudaMalloc(&d, 148 * 8);
   const int smem = 161 * 1024 + 1024;
-  int ns[4] = {64, 128, 256, 32};
-  for (int ni = 0; ni < 4; ++ni)
+  int ns[6] = {64, 128, 256, 32, 192, 96};
+  for (int ni = 0; ni < 6; ++ni)
     for (int maj = 0; maj < 4; ++maj)
       for (int shift = 0; shift < 2; ++shift) {
         P p{ns[ni], maj & 1, maj >> 1, 2000, shift * 33};
@@ -59,7 +59,7 @@ int main() {
           cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
           kern<<<148, 128, smem>>>(p, d);
         };
-        if (p.n == 64) launch(probe<64>); else if (p.n == 128) launch(probe<128>); else if (p.n == 256) launch(probe<256>); else launch(probe<32>);
+        if (p.n == 64) launch(probe<64>); else if (p.n == 128) launch(probe<128>); else if (p.n == 256) launch(probe<256>); else if (p.n == 192) launch(probe<192>); else if (p.n == 96) launch(probe<96>); else launch(probe<32>);
         cudaError_t e = cudaDeviceSynchronize();
         long long h[148]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
         double avg = 0; for (int i = 0; i < 148; ++i) avg += h[i]; avg /= 148;
