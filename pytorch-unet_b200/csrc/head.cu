@@ -546,11 +546,15 @@ __global__ void __launch_bounds__(kHeadThreads, 2) head_dense_kernel(HeadArgs a,
 //           registers; per pixel one LDS.128 of x and the pixel's dz give dW += dz * x and dx = mask(dz . w), and the 8 lanes
 //           of a pixel store its 128 contiguous bytes of dx.
 // ~200 (forward) / ~700 (backward) thread instructions per pixel instead of ~1400 / ~1800.
-constexpr int kPixStages = 3;
 constexpr int kPixPerBlock = 256;
 
-template <int KMAX, int C, int MODE>
-__global__ void __launch_bounds__(kHeadThreads, 2) head_pix_kernel(HeadArgs a, long long npix) {
+// KMAX = 8 (up to 8 classes): the per-thread weights of pass 2 no longer fit in registers next to the dW accumulators and
+// are read from shared memory.  SPLIT (forward modes of the split precision tier): x = hi + lo, a second ring carries the
+// lo plane and the pipeline is two stages deep so that both still fit.
+template <int KMAX, int C, int MODE, bool SPLIT>
+__global__ void __launch_bounds__(kHeadThreads, (KMAX > 4 || SPLIT) ? 1 : 2) head_pix_kernel(HeadArgs a, long long npix) {
+  constexpr int kPixStages = SPLIT ? 2 : 3;
+  constexpr bool W2REG = KMAX <= 4;           // pass 2: this lane's weights in registers (else from shared memory)
   constexpr int CH = C / 8;                   // 16-byte chunks per pixel
   constexpr int NS = kHeadThreads / CH;       // pass 2: pixel subsets
   constexpr int PPS = kPixPerBlock / NS;      // pass 2: pixels per subset (= CH)
@@ -558,7 +562,8 @@ __global__ void __launch_bounds__(kHeadThreads, 2) head_pix_kernel(HeadArgs a, l
   constexpr bool CE = MODE == HEAD_CE_FWD || MODE == HEAD_CE_BWD;
   extern __shared__ __align__(16) uint8_t pix_raw[];
   uint4* ring = reinterpret_cast<uint4*>(pix_raw);                             // [stages][256 pixels][CH]
-  float* sw = reinterpret_cast<float*>(ring + kPixStages * kPixPerBlock * CH);  // [KMAX][C], zero for k >= K
+  uint4* ring_lo = ring + (SPLIT ? kPixStages * kPixPerBlock * CH : 0);        // split tier: the lo plane, same layout
+  float* sw = reinterpret_cast<float*>(ring_lo + kPixStages * kPixPerBlock * CH);  // [KMAX][C], zero for k >= K
   float2* sdz = reinterpret_cast<float2*>(sw + KMAX * C);                       // backward: [KMAX][256] as (dz, dz) pairs
   __shared__ float redw[kHeadThreads / 32][2];
   const int K = a.k;
@@ -571,10 +576,11 @@ __global__ void __launch_bounds__(kHeadThreads, 2) head_pix_kernel(HeadArgs a, l
   if (MODE == HEAD_CE_BWD) gs = (a.gscale ? a.gscale[0] : 1.f) * a.ce_state[1];
   const long long hw = (long long)a.x.h * a.x.w;
   const uint4* __restrict__ xg = reinterpret_cast<const uint4*>(a.x.p);  // dense: pixel p, chunk j at xg[p * CH + j]
+  const uint4* __restrict__ xgl = SPLIT ? reinterpret_cast<const uint4*>(a.x.lo) : nullptr;
 
   // pass-2 role
   const int j2 = t % CH, s2 = t / CH;
-  float2 w2[BWD ? KMAX : 1][4], dw2[BWD ? KMAX : 1][4];
+  float2 w2[(BWD && W2REG) ? KMAX : 1][4], dw2[BWD ? KMAX : 1][4];
   float db_acc[KMAX];
   float loss_acc = 0.f, cnt_acc = 0.f;
 #pragma unroll
@@ -584,7 +590,8 @@ __global__ void __launch_bounds__(kHeadThreads, 2) head_pix_kernel(HeadArgs a, l
     for (int k = 0; k < KMAX; ++k)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        w2[k][e] = k < K ? make_float2(a.w[k * C + j2 * 8 + 2 * e], a.w[k * C + j2 * 8 + 2 * e + 1]) : make_float2(0.f, 0.f);
+        if (W2REG)
+          w2[k][e] = k < K ? make_float2(a.w[k * C + j2 * 8 + 2 * e], a.w[k * C + j2 * 8 + 2 * e + 1]) : make_float2(0.f, 0.f);
         dw2[k][e] = make_float2(0.f, 0.f);
       }
   }
@@ -597,8 +604,10 @@ __global__ void __launch_bounds__(kHeadThreads, 2) head_pix_kernel(HeadArgs a, l
       for (int i = 0; i < CH; ++i) {
         const int g = i * kHeadThreads + t;        // 16-byte piece of the block's 256 * CH, coalesced
         const int pl = g / CH, j = g - pl * CH;
-        if (p0 + pl < npix)
+        if (p0 + pl < npix) {
           cp_async_16(&ring[(stage * kPixPerBlock + pl) * CH + (j ^ (pl & (CH - 1)))], xg + (p0 + pl) * CH + j);
+          if (SPLIT) cp_async_16(&ring_lo[(stage * kPixPerBlock + pl) * CH + (j ^ (pl & (CH - 1)))], xgl + (p0 + pl) * CH + j);
+        }
       }
     }
     cp_async_commit();
@@ -624,7 +633,13 @@ __global__ void __launch_bounds__(kHeadThreads, 2) head_pix_kernel(HeadArgs a, l
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
           const uint4 v = rows[t * CH + (j ^ (t & (CH - 1)))];
-          const float2 x01 = bf2x_to_f2(v.x), x23 = bf2x_to_f2(v.y), x45 = bf2x_to_f2(v.z), x67 = bf2x_to_f2(v.w);
+          float2 x01 = bf2x_to_f2(v.x), x23 = bf2x_to_f2(v.y), x45 = bf2x_to_f2(v.z), x67 = bf2x_to_f2(v.w);
+          if (SPLIT) {  // x = hi + lo (exact in fp32)
+            const uint4 vl = ring_lo[(stage * kPixPerBlock + t) * CH + (j ^ (t & (CH - 1)))];
+            const float2 l01 = bf2x_to_f2(vl.x), l23 = bf2x_to_f2(vl.y), l45 = bf2x_to_f2(vl.z), l67 = bf2x_to_f2(vl.w);
+            x01.x += l01.x; x01.y += l01.y; x23.x += l23.x; x23.y += l23.y;
+            x45.x += l45.x; x45.y += l45.y; x67.x += l67.x; x67.y += l67.y;
+          }
 #pragma unroll
           for (int k = 0; k < KMAX; ++k) {
             const float4 wa = *reinterpret_cast<const float4*>(sw + k * C + j * 8);
@@ -711,10 +726,20 @@ __global__ void __launch_bounds__(kHeadThreads, 2) head_pix_kernel(HeadArgs a, l
           for (int k = 0; k < KMAX; ++k) {
             const float2 d = sdz[k * kPixPerBlock + pl];
             if (j2 == 0) db_acc[k] += d.x;
+            float2 wk[4];
+            if (W2REG) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) wk[e] = w2[k][e];
+            } else {
+              const float4 wa = *reinterpret_cast<const float4*>(sw + k * C + j2 * 8);
+              const float4 wb = *reinterpret_cast<const float4*>(sw + k * C + j2 * 8 + 4);
+              wk[0] = make_float2(wa.x, wa.y); wk[1] = make_float2(wa.z, wa.w);
+              wk[2] = make_float2(wb.x, wb.y); wk[3] = make_float2(wb.z, wb.w);
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               dw2[k][e] = ffma2(d, x2[e], dw2[k][e]);
-              r2[e] = ffma2(d, w2[k][e], r2[e]);
+              r2[e] = ffma2(d, wk[e], r2[e]);
             }
           }
           if (dxg) {
@@ -787,8 +812,8 @@ __global__ void __launch_bounds__(kHeadThreads, 2) head_pix_kernel(HeadArgs a, l
   }
 }
 
-inline size_t head_pix_smem(int c, int kmax, bool bwd) {
-  const size_t ring = (size_t)kPixStages * kPixPerBlock * c * 2;
+inline size_t head_pix_smem(int c, int kmax, bool bwd, bool split) {
+  const size_t ring = (size_t)(split ? 2 * 2 : 3) * kPixPerBlock * c * 2;
   const size_t tail = (size_t)kmax * c * 4 + (bwd ? (size_t)kmax * kPixPerBlock * 8 : 0);
   const size_t red = bwd ? (size_t)(kHeadThreads / (c / 8)) * kmax * (c + 1) * 4 : 0;  // aliases the ring after the loop
   return (ring > red ? ring : red) + tail;
@@ -875,16 +900,16 @@ __global__ void head_bwd_finalize_kernel(const float* __restrict__ ws, int block
     db[q - kc] = (float)s;
 }
 
-template <int MODE, int KMAX, int CC>
+template <int MODE, int KMAX, int CC, bool SPLIT>
 void launch_head_pix_inst(const HeadArgs& a, int blocks, long long npix, cudaStream_t st) {
   constexpr bool BWD = MODE == HEAD_BWD || MODE == HEAD_CE_BWD;
-  const size_t smem = head_pix_smem(CC, KMAX, BWD);
+  const size_t smem = head_pix_smem(CC, KMAX, BWD, SPLIT);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(head_pix_kernel<KMAX, CC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(head_pix_kernel<KMAX, CC, MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_done = true;
   }
-  head_pix_kernel<KMAX, CC, MODE><<<blocks, kHeadThreads, smem, st>>>(a, npix);
+  head_pix_kernel<KMAX, CC, MODE, SPLIT><<<blocks, kHeadThreads, smem, st>>>(a, npix);
 }
 
 static int g_head_pix = getenv("B200UNET_NO_HEAD_PIX") ? 0 : 1;
@@ -894,22 +919,35 @@ template <int MODE>
 bool launch_head_pix(const HeadArgs& a, int* blocks_io, cudaStream_t st) {
   constexpr bool BWD = MODE == HEAD_BWD || MODE == HEAD_CE_BWD;
   const int c = a.x.c, K = a.k;
-  if (!g_head_pix || !(c == 16 || c == 32 || c == 64) || K > 4 || a.x.lo || !dense_nhwc(a.x)) return false;
-  if (reinterpret_cast<uintptr_t>(a.x.p) % 16) return false;
+  if (!g_head_pix || !(c == 16 || c == 32 || c == 64) || K > 8 || !dense_nhwc(a.x)) return false;
+  if (reinterpret_cast<uintptr_t>(a.x.p) % 16 || reinterpret_cast<uintptr_t>(a.x.lo) % 16) return false;
+  const bool split = !BWD && a.x.lo != nullptr;  // the backward entry points read the hi plane only
   if (BWD) {
     if (a.dx.p && (!dense_nhwc(a.dx) || reinterpret_cast<uintptr_t>(a.dx.p) % 16)) return false;
-    if (a.mask && a.mask != a.x.p) return false;  // a separate mask tensor (BatchNorm graphs): general kernel
+    if (a.mask && a.mask != a.x.p) return false;  // a separate mask tensor: general kernel
   }
   const long long npix = (long long)a.x.n * a.x.h * a.x.w;
   long long blocks = (npix + kPixPerBlock - 1) / kPixPerBlock;
-  if (blocks > 2 * kNumSMsB200) blocks = 2 * kNumSMsB200;  // persistent: two blocks per SM
+  const int per_sm = (K > 4 || split) ? 1 : 2;
+  if (blocks > per_sm * kNumSMsB200) blocks = per_sm * kNumSMsB200;  // persistent
   if (blocks < 1) blocks = 1;
   *blocks_io = (int)blocks;
-  const int kmax = K <= 2 ? 2 : 4;
-#define B200_HP(KM, CC) launch_head_pix_inst<MODE, KM, CC>(a, (int)blocks, npix, st)
-  if (c == 64) { if (kmax == 2) B200_HP(2, 64); else B200_HP(4, 64); }
-  else if (c == 32) { if (kmax == 2) B200_HP(2, 32); else B200_HP(4, 32); }
-  else { if (kmax == 2) B200_HP(2, 16); else B200_HP(4, 16); }
+  const int kmax = K <= 2 ? 2 : (K <= 4 ? 4 : 8);
+#define B200_HP(KM, CC)                                                        \
+  do {                                                                         \
+    if (split) launch_head_pix_inst<MODE, KM, CC, !BWD>(a, (int)blocks, npix, st); \
+    else launch_head_pix_inst<MODE, KM, CC, false>(a, (int)blocks, npix, st);  \
+  } while (0)
+#define B200_HP_C(CC)                         \
+  do {                                        \
+    if (kmax == 2) B200_HP(2, CC);            \
+    else if (kmax == 4) B200_HP(4, CC);       \
+    else B200_HP(8, CC);                      \
+  } while (0)
+  if (c == 64) B200_HP_C(64);
+  else if (c == 32) B200_HP_C(32);
+  else B200_HP_C(16);
+#undef B200_HP_C
 #undef B200_HP
   return true;
 }
