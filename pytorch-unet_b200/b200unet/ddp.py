@@ -42,6 +42,9 @@ class GradBucketer:
         # deferred mode (b200unet.GraphedTrainStep): backward only fills the arena; the caller reduces it in ONE collective
         # between two CUDA graphs (a NCCL call issued from inside a stream capture deadlocked with the async bucket logic)
         self.defer = False
+        # streams other than the current one that write gradients (UNet's side stream for overlapped backward-weights): a
+        # bucket's reduction is ordered after everything enqueued on them so far
+        self.sync_streams: list = []
         self.deferred_arena: Optional[torch.Tensor] = None
         self._prof: List[Tuple[torch.cuda.Event, torch.cuda.Event]] = []
         self.names = list(names)
@@ -98,6 +101,9 @@ class GradBucketer:
             return
         s, e, _ = self.buckets[b]
         buf = self.arena[s:e]
+        if buf.is_cuda:
+            for st in self.sync_streams:
+                torch.cuda.current_stream(buf.device).wait_stream(st)
         if self.grad_dtype == "bf16" and buf.is_cuda and self._nccl:
             # half the bytes on the wire: the bucket travels as bf16 and is widened back after the reduction
             wire = buf.to(torch.bfloat16)
@@ -170,6 +176,7 @@ class DataParallel(torch.nn.Module):
         module._grad_alloc = self.bucketer.alloc
         module._grad_ready = self.bucketer.ready
         module._grads_done = self.bucketer.finish
+        self.bucketer.sync_streams = module._side_streams  # the same list object: filled lazily by the module
 
     def forward(self, x):
         return self.module(x)

@@ -16,6 +16,8 @@ hand-scheduled reverse pass, so that
 """
 from __future__ import annotations
 
+import os
+
 from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
@@ -202,7 +204,18 @@ class UNet(nn.Module):
         self._grads_done: Optional[Callable[[], None]] = None
         self._pack_cache: Dict[Tuple[str, int], dict] = {}
         self._nbt_pending: List[torch.Tensor] = []
+        # backward: the encoder's first-convolution backward-weights launches run on a side stream, next to the HBM-bound pool
+        # backward that follows them on the critical path (B200UNET_NO_SIDE_STREAM=1 disables)
+        self.side_stream_wgrad = os.environ.get("B200UNET_NO_SIDE_STREAM") is None
+        self._side_streams: List[torch.cuda.Stream] = []   # shared with the data-parallel bucketer (it orders reductions after them)
+        self._side_keep: List[object] = []
         self._train_forwards = 0  # training-mode forwards so far: eval-mode packs are reused only within one value
+
+    def __getstate__(self):
+        # CUDA streams cannot be pickled / deep-copied (copy.deepcopy(model), torch.save(model)); they are created lazily
+        state = dict(self.__dict__)
+        state["_side_streams"], state["_side_keep"] = [], []
+        return state
 
     # ---------------------------------------------------------------- public API
     def invalidate_packs(self) -> None:
@@ -380,6 +393,11 @@ class UNet(nn.Module):
             self._pack_cache[key] = new
         return packed
 
+    def _side_stream(self, device) -> torch.cuda.Stream:
+        if not self._side_streams:
+            self._side_streams.append(torch.cuda.Stream(device=device))
+        return self._side_streams[0]
+
     def _new_grad(self, name: str, like: torch.Tensor) -> torch.Tensor:
         """Gradient buffer for parameter `name` (`like` has the shape the kernels produce, i.e. the padded one)."""
         if name in self._padspec:  # kernels write the padded gradient into a scratch tensor, _done() un-pads it
@@ -515,7 +533,8 @@ class UNet(nn.Module):
         return loss
 
     # ---------------------------------------------------------------- backward
-    def _block_backward(self, prefix: str, blk: UNetConvBlock, tape, P, g, grads, src_dsts, src_masks):
+    def _block_backward(self, prefix: str, blk: UNetConvBlock, tape, P, g, grads, src_dsts, src_masks,
+                        overlap_wgrad: bool = False):
         """Reverse of _block_forward.  `g` = gradient w.r.t. the block output (already ReLU-masked when there is no
         BatchNorm).  src_dsts: destination tensors for the gradient of each source (None = not needed)."""
         rec = tape.blocks.pop(prefix)
@@ -538,16 +557,23 @@ class UNet(nn.Module):
             srcs = rec["srcs"] if i == 0 else [rec["o0"]]
             dw = self._new_grad(names[i] + ".weight", w)
             db = self._new_grad(names[i] + ".bias", P[names[i] + ".bias"])
+            side = None
+            if (i == 0 and overlap_wgrad and src_dsts is not None and self.side_stream_wgrad and dz.is_cuda
+                    and (names[i] + ".weight") not in self._padspec):  # padded gradients are un-padded on this stream at once
+                # critical path first: backward-data of this convolution feeds the pool backward of the level above, which
+                # is HBM-bound; this convolution's backward-weights (tensor-bound, nobody waits for it) then runs next to
+                # it on a side stream instead of in front of it
+                side = self._side_stream(dz.device)
             if i == 0 and self._first_layer_patches(prefix, srcs, w):
                 # 1..7 input channels: the 3x3 patch (9*Cin values) fits one 64-wide K chunk, so backward-weights of
                 # the first layer runs as a 1x1 problem on the tensor-core kernel over the im2col'ed image (built here,
                 # 2*Kp bytes per pixel, dropped right after).  Measured 0.77 ms vs 1.24 ms for the CUDA-core kernel at
-                # batch 32; the forward stays on the CUDA-core first-layer kernel (0.70 ms vs 0.81 ms through im2col).
+                # batch 32; the forward stays on the first-layer kernel.
                 patches = ops.im2col3x3(srcs[0], pad)
                 dw1, _ = ops.conv_wgrad(dz, [patches], 1, 0, impl=self.conv_impl, db=db)
                 dw.copy_(dw1[:, :w.shape[1] * 9, 0, 0].reshape(w.shape))
                 del patches
-            else:
+            elif side is None:
                 ops.conv_wgrad(dz, srcs, 3, pad, impl=self.conv_impl, dw=dw, db=db)
             grads[names[i] + ".weight"], grads[names[i] + ".bias"] = dw, db
             if i == 1:
@@ -565,6 +591,13 @@ class UNet(nn.Module):
                 else:
                     ops.conv_dgrad(dz, w.detach(), pad, src_dsts, src_masks, impl=self.conv_impl,
                                    w_packed=lambda: self._packed(names[i] + ".weight", w, 1))
+            if side is not None:
+                main = torch.cuda.current_stream(dz.device)
+                side.wait_stream(main)       # dz (and everything before it) is complete for the side stream
+                with torch.cuda.stream(side):
+                    ops.conv_wgrad(dz, srcs, 3, pad, impl=self.conv_impl, dw=dw, db=db)
+                # the caching allocator must not hand these buffers to main-stream work before the side kernel has read them
+                self._side_keep.extend([dz, dw, db] + [ops.hi_of(t) for t in srcs])
             self._done(*( [bn_names[i] + ".weight", bn_names[i] + ".bias"] if blk.batch_norm else [] ),
                        names[i] + ".weight", names[i] + ".bias")
 
@@ -659,8 +692,11 @@ class UNet(nn.Module):
             else:
                 prev_pooled_shape = tape.blocks[f"down_path.{i}"]["srcs"][0].shape
                 gp = torch.empty(prev_pooled_shape, dtype=torch.bfloat16, device=g.device)
-                self._block_backward(f"down_path.{i}", down, tape, P, g, grads, [gp], [None])
+                self._block_backward(f"down_path.{i}", down, tape, P, g, grads, [gp], [None], overlap_wgrad=True)
                 g = gp
+        if self._side_streams and self._side_keep:
+            torch.cuda.current_stream(g.device).wait_stream(self._side_streams[0])  # join: every gradient is complete
+            self._side_keep = []
         if self._grads_done is not None:
             self._grads_done()
         self._cur_grads = {}
