@@ -419,10 +419,11 @@ def relu_mask(x, mask, out=None):
     return out
 
 
-def channel_sum(x) -> torch.Tensor:
+def channel_sum(x, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     lib = _lib.load()
     c = x.shape[3]
-    out = torch.empty(c, dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty(c, dtype=torch.float32, device=x.device)
     ws = workspace(lib.b200unet_bn_workspace_bytes(c), x.device)
     vx = view(x)
     check(lib.b200unet_channel_sum(C.byref(vx), out.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr()),

@@ -651,7 +651,17 @@ class UNet(nn.Module):
                 w = P[wn + ".weight"]
                 dw = self._new_grad(wn + ".weight", w)
                 db = self._new_grad(wn + ".bias", P[wn + ".bias"])
-                ops.convt_wgrad(xin, d_up, impl=self.conv_impl, dw=dw, db=db)
+                if self.side_stream_wgrad and d_up.is_cuda and (wn + ".bias") not in self._padspec:
+                    # the bias gradient (a column sum over d_up: HBM-bound) runs on the side stream next to the L2-fed
+                    # tensor-core kernels below instead of after them
+                    side = self._side_stream(d_up.device)
+                    side.wait_stream(torch.cuda.current_stream(d_up.device))
+                    with torch.cuda.stream(side):
+                        ops.channel_sum(d_up, out=db)
+                    self._side_keep.extend([d_up, db])
+                    ops.convt_wgrad(xin, d_up, want_db=False, impl=self.conv_impl, dw=dw)
+                else:
+                    ops.convt_wgrad(xin, d_up, impl=self.conv_impl, dw=dw, db=db)
                 ops.convt_dgrad(d_up, w.detach(), g, mask=xmask, impl=self.conv_impl,
                                 w_packed=lambda: self._packed(wn + ".weight", w, 1, transposed_conv=True))
             else:
