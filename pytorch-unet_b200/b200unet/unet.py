@@ -209,6 +209,7 @@ class UNet(nn.Module):
         self.side_stream_wgrad = os.environ.get("B200UNET_NO_SIDE_STREAM") is None
         self._side_streams: List[torch.cuda.Stream] = []   # shared with the data-parallel bucketer (it orders reductions after them)
         self._side_keep: List[object] = []
+        self._overlap_first = os.environ.get("B200UNET_NO_OVERLAP_FIRST") is None
         self._train_forwards = 0  # training-mode forwards so far: eval-mode packs are reused only within one value
 
     def __getstate__(self):
@@ -558,6 +559,13 @@ class UNet(nn.Module):
             dw = self._new_grad(names[i] + ".weight", w)
             db = self._new_grad(names[i] + ".bias", P[names[i] + ".bias"])
             side = None
+            if (i == 1 and prefix == "down_path.0" and self.side_stream_wgrad and self._overlap_first and dz.is_cuda
+                    and not blk.batch_norm and (names[i] + ".weight") not in self._padspec
+                    and self._first_layer_patches(prefix, rec["srcs"], P[names[0] + ".weight"])):
+                # last block of the backward pass: its second convolution's backward-weights (tensor-bound) goes to the side
+                # stream, next to the first layer's backward-weights that follows on this one (im2col + a K = 16 GEMM over the
+                # full-resolution gradient: HBM-bound)
+                side = self._side_stream(dz.device)
             if (i == 0 and overlap_wgrad and src_dsts is not None and self.side_stream_wgrad and dz.is_cuda
                     and (names[i] + ".weight") not in self._padspec):  # padded gradients are un-padded on this stream at once
                 # critical path first: backward-data of this convolution feeds the pool backward of the level above, which
