@@ -11,7 +11,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200unet.so")
+LIB_PATH = os.environ.get("B200UNET_LIB") or os.path.join(_HERE, "libb200unet.so")  # override: A/B builds of the same ABI
 
 IMPL_AUTO, IMPL_DIRECT, IMPL_UMMA = 0, 1, 2
 

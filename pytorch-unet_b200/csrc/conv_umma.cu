@@ -249,6 +249,10 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
       for (int s = 0; s < a.num_a; ++s) {
         for (int c0 = 0; c0 < a.a_c[s]; c0 += 64) {
           mbar_wait(&a_full[astage], aphase);
+          // K steps of 16 channels that hold real data in this chunk: narrow layers (16 / 32 channels: the feature net, the
+          // first levels of wf = 5 networks) load a 64-wide box whose tail is TMA zero fill — issuing MMAs on it was 2-4x
+          // the necessary tensor work
+          const int c_left = a.a_c[s] - c0;  // K step kk holds data iff 16 * kk < c_left
           const uint32_t a_base = smem_u32(sA + astage * a_stage_bytes);
           int tap_s = -1;
           uint32_t tap_row_off = 0;
@@ -266,20 +270,39 @@ umma_conv_kernel(const __grid_constant__ TileMaps maps, const __grid_constant__ 
             const uint64_t a_desc = a_desc0 + tap_row_off;
             const uint64_t b_desc = umma_desc(desc_hi, smem_u32(sB + bstage * B_STAGE_BYTES));
             if (elect_one()) {
+              if (c_left >= 64) {  // full chunk: the unpredicated sequence (the issuing lane has 48 cycles per N = 64 MMA)
 #pragma unroll
-              for (int mb = 0; mb < MB; ++mb) {
-                // M-block m starts 128 rows (16 KiB -> 1024 in the >>4 address field) further; K step = 32 B -> 2.
-                // The first MMA into each M-block's accumulator overwrites, everything after accumulates.
-                if (CL == 2) {
-                  umma_bf16_2cta(acc + mb * BN, a_desc + (uint64_t)mb * 1024, b_desc, idesc, accum);
+                for (int mb = 0; mb < MB; ++mb) {
+                  // M-block m starts 128 rows (16 KiB -> 1024 in the >>4 address field) further; K step = 32 B -> 2.
+                  // The first MMA into each M-block's accumulator overwrites, everything after accumulates.
+                  if (CL == 2) {
+                    umma_bf16_2cta(acc + mb * BN, a_desc + (uint64_t)mb * 1024, b_desc, idesc, accum);
 #pragma unroll
-                  for (int kk = 1; kk < 4; ++kk)
-                    umma_bf16_2cta(acc + mb * BN, a_desc + (uint64_t)(mb * 1024 + kk * 2), b_desc + (uint64_t)(kk * 2), idesc, 1u);
-                } else {
-                  umma_bf16(acc + mb * BN, a_desc + (uint64_t)mb * 1024, b_desc, idesc, accum);
+                    for (int kk = 1; kk < 4; ++kk)
+                      umma_bf16_2cta(acc + mb * BN, a_desc + (uint64_t)(mb * 1024 + kk * 2), b_desc + (uint64_t)(kk * 2), idesc, 1u);
+                  } else {
+                    umma_bf16(acc + mb * BN, a_desc + (uint64_t)mb * 1024, b_desc, idesc, accum);
 #pragma unroll
-                  for (int kk = 1; kk < 4; ++kk)
-                    umma_bf16(acc + mb * BN, a_desc + (uint64_t)(mb * 1024 + kk * 2), b_desc + (uint64_t)(kk * 2), idesc, 1u);
+                    for (int kk = 1; kk < 4; ++kk)
+                      umma_bf16(acc + mb * BN, a_desc + (uint64_t)(mb * 1024 + kk * 2), b_desc + (uint64_t)(kk * 2), idesc, 1u);
+                  }
+                }
+              } else {  // narrow chunk: only the K steps that hold data
+#pragma unroll
+                for (int mb = 0; mb < MB; ++mb) {
+                  if (CL == 2) {
+                    umma_bf16_2cta(acc + mb * BN, a_desc + (uint64_t)mb * 1024, b_desc, idesc, accum);
+#pragma unroll
+                    for (int kk = 1; kk < 4; ++kk)
+                      if (16 * kk < c_left)
+                        umma_bf16_2cta(acc + mb * BN, a_desc + (uint64_t)(mb * 1024 + kk * 2), b_desc + (uint64_t)(kk * 2), idesc, 1u);
+                  } else {
+                    umma_bf16(acc + mb * BN, a_desc + (uint64_t)mb * 1024, b_desc, idesc, accum);
+#pragma unroll
+                    for (int kk = 1; kk < 4; ++kk)
+                      if (16 * kk < c_left)
+                        umma_bf16(acc + mb * BN, a_desc + (uint64_t)(mb * 1024 + kk * 2), b_desc + (uint64_t)(kk * 2), idesc, 1u);
+                  }
                 }
               }
               if (CL == 2)

@@ -52,10 +52,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
+#ifdef B200_MBAR_SUSPEND_HINT
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+#else
       "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+#endif
       "selp.u32 %0, 1, 0, P;\n\t}\n"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
+#ifdef B200_MBAR_SUSPEND_HINT
+        , "r"((uint32_t)B200_MBAR_SUSPEND_HINT)
+#endif
       : "memory");
   return ok != 0;
 }
