@@ -650,8 +650,10 @@ def run_ours(args, cfg):
     conv_ms = sum(r[6] for r in recs if r[0] in OpTimer.CONV) / steps
     step_split = {"conv3x3_ms": ms3, "conv_family_ms": conv_ms,
                   "hbm_ops_ms": sum(v["ms_per_step"] for v in hbm_kernels.values()),
-                  "other_ms": ms - conv_ms - sum(v["ms_per_step"] for k, v in hbm_kernels.items() if k != "first_layer_fwd"),
-                  "note": "other = optimizer, weight-gradient reductions outside the bracketed calls, launch gaps"}
+                  "other_ms": (ms_instr if ms_instr is not None else ms) - conv_ms -
+                              sum(v["ms_per_step"] for k, v in hbm_kernels.items() if k != "first_layer_fwd"),
+                  "note": "split of the instrumented pass (roofline.instrumented_ms_per_step); other = optimizer, "
+                          "weight-gradient reductions outside the bracketed calls, launch gaps"}
 
     cpu = None
     if world == 1 and not args.no_cpu:

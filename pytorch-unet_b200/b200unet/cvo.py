@@ -120,31 +120,32 @@ def cross_subtract(pcl_1: torch.Tensor, pcl_2: torch.Tensor) -> torch.Tensor:
     return _cross(pcl_1, pcl_2, True, "cross_subtract")
 
 
-def gramian(fea_flat_1, fea_flat_2, norm_mode, kernalize, norm_dim, dist_coef=1e0):
-    """geometry.py:138-181, same arguments and both return values; the O(N1*N2) part is kern_mat above (or the
-    plain matmul when `kernalize` is false), the O(N) normalisations are torch glue as in the reference."""
-    fea_norm_sum_1 = torch.zeros((), dtype=fea_flat_1.dtype, device=fea_flat_1.device)
-    fea_norm_sum_2 = torch.zeros((), dtype=fea_flat_2.dtype, device=fea_flat_2.device)
+def _feature_norm(f: torch.Tensor, norm_dim: int):
+    """The per-pixel L2 norm over channels (norm_dim 1) or the per-channel mean |.| over pixels (norm_dim 2)."""
     if norm_dim == 1:
-        fea_norm_1 = torch.norm(fea_flat_1, dim=1, keepdim=True)
-        fea_norm_2 = torch.norm(fea_flat_2, dim=1, keepdim=True)
-    elif norm_dim == 2:
-        fea_norm_1 = torch.mean(torch.abs(fea_flat_1), dim=2, keepdim=True)
-        fea_norm_2 = torch.mean(torch.abs(fea_flat_2), dim=2, keepdim=True)
+        return f.norm(dim=1, keepdim=True)
+    if norm_dim == 2:
+        return f.abs().mean(dim=2, keepdim=True)
+    return None
+
+
+def gramian(fea_flat_1, fea_flat_2, norm_mode, kernalize, norm_dim, dist_coef=1e0):
+    """geometry.py:138-181 with the same arguments and both return values (Gramian, norm penalty).  The O(N1*N2) part is
+    `kern_mat` above (or a plain matmul when `kernalize` is false); the O(N) feature normalisation stays in torch."""
+    feats = [fea_flat_1, fea_flat_2]
+    norms = [_feature_norm(f, norm_dim) for f in feats]
+    penalty = [torch.zeros((), dtype=f.dtype, device=f.device) for f in feats]
     if norm_mode:
-        fea_flat_1 = torch.div(fea_flat_1, fea_norm_1)
-        fea_flat_2 = torch.div(fea_flat_2, fea_norm_2)
-        if norm_dim == 2:
-            fea_norm_sum_1 = -torch.mean(torch.norm(fea_flat_1, dim=2))
-            fea_norm_sum_2 = -torch.mean(torch.norm(fea_flat_2, dim=2))
+        feats = [f / n for f, n in zip(feats, norms)]          # the reference divides without an epsilon
+        if norm_dim == 2:                                       # sparsity measure of the normalised maps
+            penalty = [-f.norm(dim=2).mean() for f in feats]
     elif norm_dim in (1, 2):
-        fea_norm_sum_1 = torch.mean(fea_norm_1)
-        fea_norm_sum_2 = torch.mean(fea_norm_2)
-    if not kernalize:
-        g = torch.matmul(fea_flat_1.transpose(1, 2), fea_flat_2)
+        penalty = [n.mean() for n in norms]
+    if kernalize:
+        g = kern_mat(feats[0], feats[1], dist_coef=dist_coef)
     else:
-        g = kern_mat(fea_flat_1, fea_flat_2, dist_coef=dist_coef)
-    return g, fea_norm_sum_1 + fea_norm_sum_2
+        g = torch.matmul(feats[0].transpose(1, 2), feats[1])
+    return g, penalty[0] + penalty[1]
 
 
 # ------------------------------------------------------------------------------------------------ fused inner product
