@@ -68,15 +68,41 @@ __device__ __forceinline__ void adam_tile(const b200_adam_job& J, const AdamCoef
   const int a0 = (blk / tiles_b) * kTileA, b0 = (blk % tiles_b) * kTileB;
   const int nb = FULL ? kTileB : min(kTileB, B - b0), na = FULL ? kTileA : min(kTileA, A - a0);
   const int run = nb * T;  // contiguous floats per a-row
-  for (int idx = threadIdx.x; idx < na * run; idx += kAdamThreads) {
-    const int al = idx / run, r = idx - al * run;
-    const long long i = ((long long)(a0 + al) * B + b0) * T + r;
-    float m = J.exp_avg[i], v = J.exp_avg_sq[i];
-    const float p = adam_update(c, J.param[i], J.grad[i], m, v);
-    J.param[i] = p;
-    J.exp_avg[i] = m;
-    J.exp_avg_sq[i] = v;
-    tile[al][r] = p;
+  const bool al16 = ((reinterpret_cast<uintptr_t>(J.param) | reinterpret_cast<uintptr_t>(J.grad) |
+                      reinterpret_cast<uintptr_t>(J.exp_avg) | reinterpret_cast<uintptr_t>(J.exp_avg_sq)) & 15) == 0;
+  if (FULL && B % 4 == 0 && al16) {
+    // complete tile: a row is 32 * T contiguous floats starting at a multiple of 16 bytes -> four tensors x one 16-byte
+    // access per thread and iteration instead of sixteen 4-byte ones (the kernel ran at 2.9 TB/s on scalar accesses)
+    constexpr int RUN4 = kTileB * T / 4;
+    for (int idx = threadIdx.x; idx < kTileA * RUN4; idx += kAdamThreads) {
+      const int al = idx / RUN4, r4 = idx - al * RUN4;
+      const long long i = ((long long)(a0 + al) * B + b0) * T + 4 * r4;
+      const float4 p4 = *reinterpret_cast<const float4*>(J.param + i), g4 = *reinterpret_cast<const float4*>(J.grad + i);
+      float4 m4 = *reinterpret_cast<const float4*>(J.exp_avg + i), v4 = *reinterpret_cast<const float4*>(J.exp_avg_sq + i);
+      float4 o;
+      o.x = adam_update(c, p4.x, g4.x, m4.x, v4.x);
+      o.y = adam_update(c, p4.y, g4.y, m4.y, v4.y);
+      o.z = adam_update(c, p4.z, g4.z, m4.z, v4.z);
+      o.w = adam_update(c, p4.w, g4.w, m4.w, v4.w);
+      *reinterpret_cast<float4*>(J.param + i) = o;
+      *reinterpret_cast<float4*>(J.exp_avg + i) = m4;
+      *reinterpret_cast<float4*>(J.exp_avg_sq + i) = v4;
+      tile[al][4 * r4 + 0] = o.x;
+      tile[al][4 * r4 + 1] = o.y;
+      tile[al][4 * r4 + 2] = o.z;
+      tile[al][4 * r4 + 3] = o.w;
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < na * run; idx += kAdamThreads) {
+      const int al = idx / run, r = idx - al * run;
+      const long long i = ((long long)(a0 + al) * B + b0) * T + r;
+      float m = J.exp_avg[i], v = J.exp_avg_sq[i];
+      const float p = adam_update(c, J.param[i], J.grad[i], m, v);
+      J.param[i] = p;
+      J.exp_avg[i] = m;
+      J.exp_avg_sq[i] = v;
+      tile[al][r] = p;
+    }
   }
   __syncthreads();
   bf16* pf = reinterpret_cast<bf16*>(J.pack_fwd);
