@@ -41,6 +41,24 @@ def _worker(rank, world, port, out):
         for i, n in enumerate(names):
             want = sum(float(r + 1) * (i + 1) + step for r in range(world)) / world
             assert torch.allclose(grads[n], torch.full(shapes[n], want)), (n, grads[n].flatten()[0].item(), want)
+    # deferred mode (GraphedTrainStep over DataParallel): backward only fills the arena, ONE collective reduces it afterwards
+    gb.defer = True
+    gb.begin("cpu")
+    grads = {}
+    for i, n in enumerate(names):
+        g = gb.alloc(n, shapes[n], "cpu")
+        g.fill_(float(rank + 1) * (i + 1))
+        grads[n] = g
+        gb.ready(n)                      # must NOT start a reduction
+    gb.finish()
+    arena = gb.deferred_arena
+    assert arena is not None and gb.arena is None
+    i0 = names.index(names[0])
+    assert torch.allclose(grads[names[0]], torch.full(shapes[names[0]], float(rank + 1) * (i0 + 1)))   # still local
+    gb.reduce_all(arena)
+    for i, n in enumerate(names):
+        want = sum(float(r + 1) * (i + 1) for r in range(world)) / world
+        assert torch.allclose(grads[n], torch.full(shapes[n], want)), n
     out.put((rank, "ok"))
     dist.destroy_process_group()
 
