@@ -307,7 +307,8 @@ class OpTimer:
         if name == "maxpool_bwd":
             dy, idx, dx = a[0], a[1], a[2]
             add = a[3] if len(a) > 3 else kw.get("add")
-            return 0.0, _planes(dy) + idx.numel() + _planes(dx) + _planes(add) + _planes(kw.get("mask")), 0, shp, ()
+            return (0.0, _planes(dy) + idx.numel() + _planes(dx) + _planes(add) + _planes(kw.get("mask")) +
+                    _planes(kw.get("pooled")), 0, shp, ())
         if name == "bilinear_fwd":
             return 0.0, _planes(x) + _planes(ret), 0, shp, ()
         if name == "bilinear_bwd":
